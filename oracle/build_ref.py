@@ -1,0 +1,72 @@
+"""Build the UNMODIFIED reference extensions from /root/reference into oracle/_ref/.
+
+TEST INFRASTRUCTURE ONLY. Nothing under oracle/ is imported by the product package.
+
+Outputs (git-ignored, but they travel to the GPU box with the gpurun snapshot):
+  oracle/_ref/PCONV_ref.so  - the reference CUDA extension (extension/*.cu, main.cpp), compiled
+                              for sm_100 exactly as SURVEY.md fact 9 describes: same sources,
+                              nvcc defaults (-fmad=true), only -std=c++17 and the gencode differ
+                              from the reference's setup.py:10-17.
+  oracle/_ref/coder_ref.so  - the reference host arithmetic coder (coder/*.cpp).
+
+The sources are compiled where they lie; no reference source is copied into this repository.
+The modules are renamed through -DTORCH_EXTENSION_NAME so they can be imported next to the
+product's own `PCONV` / `coder` mirrors.
+"""
+import os
+import sys
+
+REF = os.environ.get("PCX_REFERENCE_ROOT", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "_ref")
+
+EXT_SOURCES = [
+    "main.cpp", "math_cuda.cu", "projects_cuda.cu", "dtow_cuda.cu", "context_reshape_cuda.cu",
+    "entropy_gmm_cuda.cu", "mask_constrain_cuda.cu", "sphere_slice_cuda.cu", "sphere_uslice_cuda.cu",
+    "entropy_gmm_table_cuda.cu", "entropy_context_cuda.cu", "entropy_ctx_pad_run2_cuda.cu",
+    "d_extract_cuda_v2.cu", "d_input_cuda_v2.cu", "entropy_conv_cuda_v2.cu", "pseudo_context_cuda.cu",
+    "pseudo_pad.cu", "pseudo_fill_cuda.cu", "pseudo_entropy_context_cuda.cu", "pseudo_entropy_pad_cuda.cu",
+    "pseudo_quant_cuda.cu", "pseudo_dquant_cuda.cu", "string2class.cc", "entropy_add_cuda.cu",
+]
+CODER_SOURCES = ["python.cpp", "ArithmeticCoder.cpp", "BitIoStream.cpp"]
+
+
+def build(which=("coder", "pconv"), verbose=False):
+    if not os.path.isdir(REF):
+        print(f"[build_ref] {REF} not present - keeping whatever is prebuilt in {OUT}")
+        return False
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
+    os.environ.setdefault("MAX_JOBS", str(os.cpu_count() or 4))
+    from torch.utils import cpp_extension as ce
+    os.makedirs(OUT, exist_ok=True)
+    if "coder" in which:
+        bd = os.path.join(OUT, "build_coder")
+        os.makedirs(bd, exist_ok=True)
+        ce.load(name="coder_ref", sources=[os.path.join(REF, "coder", s) for s in CODER_SOURCES],
+                extra_cflags=["-O2", "-std=c++17"], build_directory=bd, is_python_module=False,
+                verbose=verbose)
+        _publish(bd, "coder_ref")
+    if "pconv" in which:
+        bd = os.path.join(OUT, "build_pconv")
+        os.makedirs(bd, exist_ok=True)
+        ce.load(name="PCONV_ref", sources=[os.path.join(REF, "extension", s) for s in EXT_SOURCES],
+                extra_include_paths=[os.path.join(REF, "extension")],
+                extra_cflags=["-std=c++17", "-DOK"],
+                extra_cuda_cflags=["-std=c++17", "-D__CUDA_NO_HALF_OPERATORS__",
+                                   "-gencode", "arch=compute_100,code=sm_100"],
+                build_directory=bd, is_python_module=False, with_cuda=True, verbose=verbose)
+        _publish(bd, "PCONV_ref")
+    return True
+
+
+def _publish(build_dir, name):
+    import shutil
+    src = os.path.join(build_dir, name + ".so")
+    dst = os.path.join(OUT, name + ".so")
+    shutil.copyfile(src, dst)
+    print(f"[build_ref] {dst}")
+
+
+if __name__ == "__main__":
+    which = tuple(sys.argv[1:]) or ("coder", "pconv")
+    build(which, verbose=True)

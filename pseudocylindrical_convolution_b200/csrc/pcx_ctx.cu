@@ -1,0 +1,398 @@
+// pcx_ctx.cu - the masked autoregressive context model evaluated along the 3-D wavefront
+// row + column + channel-group = step, and the GMM integer CDF tables that feed the arithmetic coder.
+//
+// Every output scalar is reduced in the reference's order: 128 virtual lanes, lane
+// i < 25*gi owns tap (kw = i%5, kh = (i/5)%5, m = i/25) and chains FFMAs over the allowed channel groups in
+// ascending order; lanes fold [t]+=[t+64], [t]+=[t+32], then shuffle-down 16..1.  Here one WARP produces one
+// scalar: lane l carries virtual lanes l, l+32, l+64 in registers, so the folds are register adds and the
+// tail is the same shuffle tree - bit-identical results with a quarter of the threads and no shared memory.
+#include "pcx_common.cuh"
+
+namespace {
+
+struct Window { int first, count; };
+
+// planes [max(0, s-G+1), min(s+1, Hf+W-1)) of the wavefront order (entropy_conv_cuda_v2.cu:389-391)
+inline Window wave_window(const int *h_start, int psum, int G, int Hf, int W)
+{
+    int st = psum - G + 1 < 0 ? 0 : psum - G + 1;
+    int en = psum < Hf + W - 2 ? psum + 1 : Hf + W - 1;
+    if (st > en) st = en;
+    return {h_start[st], h_start[en] - h_start[st]};
+}
+
+inline int grid_for(i64 total, int threads)
+{
+    i64 want = (total + threads - 1) / threads;
+    return (int)(want < 1 ? 1 : (want > 0x7fffffff ? 0x7fffffff : want));
+}
+
+// ------------------------------------------------------------------------------------------------ ctx pad
+// entropy_ctx_pad_run2_forward_kernel (extension/entropy_ctx_pad_run2_cuda.cu:33-65)
+__global__ void ctx_pad_kernel(float *__restrict__ buf, Bands bands, const int *__restrict__ hband, const int *__restrict__ hrow,
+                               const int *__restrict__ hcol, const float *__restrict__ htw, const int4 *__restrict__ items,
+                               int first, int nitems, int nrep, int cpn, int C, int h, int W, int pad, int psum)
+{
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    i64 total = (i64)nitems * cpn * nrep;
+    if (idx >= total) return;
+    int it = (int)(idx % nitems);
+    int cc = (int)((idx / nitems) % cpn);
+    i64 n = idx / nitems / cpn;
+    int4 I = items[first + it];
+    const int npart = bands.npart;
+    const i64 oh = h + 2 * pad, ow = W + 2 * pad;
+    i64 c = (i64)(psum - I.w) * cpn + cc;
+    if (I.x == 0) {
+        int e = I.y, hr = I.z;
+        int g = hr / (2 * pad), s = (hr / pad) % 2, r = hr % pad, x = e % W;
+        int y = s == 0 ? r : pad + h + r;
+        int pg = hband[hr];
+        float *dst = buf + (((n * npart + g) * C + c) * oh + y) * ow + pad + x;
+        const float *src = buf + (((n * npart + pg) * C + c) * oh + pad + hrow[hr]) * ow + pad;
+        int q = hcol[e];
+        float a = (q < 0) ? 0.f : src[q];
+        int q1 = (q + 1 == bands.wl[pg]) ? 0 : q + 1;
+        *dst = lerp2_ref(a, src[q1], htw[e]);
+    } else {
+        int g = I.y, y = I.z / pad, k = I.z % pad;
+        float *rowp = buf + (((n * npart + g) * C + c) * oh + y) * ow;
+        rowp[pad + bands.wl[g] + k] = rowp[pad + k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ masked conv
+// entropy_conv2_data_to_col_gpu_v3{,_act}_batch (extension/entropy_conv_cuda_v2.cu:237-290, :326-379)
+template <int GI>
+__global__ void __launch_bounds__(256) ctx_conv_kernel(const float *__restrict__ in, const float *__restrict__ weight,
+                                                       const float *__restrict__ bias, const float *__restrict__ act,
+                                                       float *__restrict__ out, const int *__restrict__ order, int first,
+                                                       int len, int nimg, int nscalars, int npart, int G, int go, int h,
+                                                       int W, int pad_in, int pad_out, int constrain, int psum)
+{
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= nscalars) return;
+    // scalar id -> (cell k, output-in-group og, batch-image pn), cell fastest (the reference's blockIdx order)
+    const int k = wid % len;
+    const int og = (wid / len) % go;
+    const int pn = wid / len / go;
+    const int b = pn / nimg;
+    const int hw = order[first + k];
+    const int tw = hw % W, hp = hw / W, g = hp / h, th = hp % h;
+    const int tc = psum - tw - hp;
+    const int pout = tc * go + og;
+    const int Ci = G * GI, Co = G * go;
+    const i64 ih = h + 2 * pad_in, iw = W + 2 * pad_in;
+    const i64 qn = (i64)pn * npart + g;
+    const float *in_cell = in + (qn * Ci * ih + th + pad_in) * iw + tw + pad_in;
+    const float *wgt = weight + ((i64)b * Co + pout) * Ci * 25;
+
+    constexpr int NTH = 25 * GI;                 // live virtual lanes (25 or 75)
+    constexpr int NV = (NTH + 31) / 32;          // virtual lanes per physical lane (1 or 3)
+    float v[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+        const int i = lane + 32 * j;
+        if (i < NTH) {
+            const int kw = i % 5, kh = (i / 5) % 5, m = i / 25;
+            const int qh = hp - 2 + kh, pw = tw - 2 + kw;
+            int nch = (constrain == 5 ? (psum - qh - pw) : (psum - qh - pw + 1)) * GI;
+            if (nch > Ci) nch = Ci;
+            const float *ip = in_cell + (i64)(kh - 2) * iw + (kw - 2);
+            const float *wp = wgt + kh * 5 + kw;
+            float acc = 0.f;
+            for (int ti = m; ti < nch; ti += GI) acc = __fmaf_rn(ip[(i64)ti * ih * iw], wp[ti * 25], acc);
+            v[j] = acc;
+        }
+    }
+    // [t] += [t+64] (t < 64): virtual lanes l and l+32 absorb l+64 and l+96 (the latter never live)
+    float s0 = __fadd_rn(v[0], v[2]);
+    float s1 = __fadd_rn(v[1], 0.f);
+    // [t] += [t+32] (t < 32)
+    float sum = __fadd_rn(s0, s1);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum = __fadd_rn(sum, __shfl_down_sync(0xffffffffu, sum, off));
+    if (lane == 0) {
+        const i64 oh = h + 2 * pad_out, ow = W + 2 * pad_out;
+        const int bidx = b * Co + pout;
+        sum = __fadd_rn(sum, bias[bidx]);
+        if (act != nullptr && sum < 0.f) sum = __fmul_rn(sum, act[bidx]);
+        out[((qn * Co + pout) * oh + th + pad_out) * ow + tw + pad_out] = sum;
+    }
+}
+
+// entropy_add_forward_kernel (extension/entropy_add_cuda.cu:25-44)
+__global__ void ctx_add_kernel(float *__restrict__ y, const float *__restrict__ x, const int *__restrict__ order, int first,
+                               int len, int nrep, int cpg, int npart, int C, int h, int W, int pad, int psum)
+{
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (i64)len * cpg * nrep) return;
+    int pn = (int)(idx % nrep);
+    int k = (int)((idx / nrep) % len);
+    int og = (int)(idx / nrep / len);
+    int hw = order[first + k];
+    int tw = hw % W, hp = hw / W, g = hp / h, th = hp % h;
+    int tc = psum - tw - hp;
+    i64 i = ((((i64)pn * npart + g) * C + (i64)tc * cpg + og) * (h + 2 * pad) + th + pad) * (W + 2 * pad) + tw + pad;
+    y[i] = __fadd_rn(y[i], x[i]);
+}
+
+// d_input2_forward_kernel (extension/d_input_cuda_v2.cu:32-52)
+__global__ void dinput_kernel(const float *__restrict__ sym, float *__restrict__ out, const int *__restrict__ order, int first,
+                              int len, int nimg, int npart, int G, int h, int W, int pad, float bias, int rep,
+                              i64 rep_stride, int psum)
+{
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (i64)len * nimg) return;
+    int k = (int)(idx % len);
+    i64 n = idx / len;
+    int hw = order[first + k];
+    int tw = hw % W, hp = hw / W, g = hp / h, th = hp % h;
+    int tc = psum - tw - hp;
+    i64 i = (((n * npart + g) * G + tc) * (h + 2 * pad) + th + pad) * (W + 2 * pad) + tw + pad;
+    float v = __fadd_rn(sym[idx], bias);
+    for (int j = 0; j < rep; j++) out[i + j * rep_stride] = v;
+}
+
+// d_extract2_forward_kernel / d_extract2_batch_forward_kernel (extension/d_extract_cuda_v2.cu:34-52, :110-132)
+__global__ void dextract_kernel(const float *__restrict__ in, float *__restrict__ out, const int *__restrict__ order, int first,
+                                int len, int nrep, int npart, int G, int cpn, int h, int W, int psum, int nimg_batch,
+                                i64 net_stride)
+{
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (i64)len * cpn * nrep) return;
+    int ci = (int)(idx % cpn);
+    int k = (int)((idx / cpn) % len);
+    int n = (int)(idx / cpn / len);
+    int hw = order[first + k];
+    int tw = hw % W, hp = hw / W, g = hp / h, th = hp % h;
+    int tc = psum - tw - hp;
+    float v = in[((((i64)n * npart + g) * G * cpn + (i64)tc * cpn + ci) * h + th) * W + tw];
+    if (nimg_batch > 0) out[(n / nimg_batch) * net_stride + (((i64)(n % nimg_batch) * len + k) * cpn + ci)] = v;
+    else out[idx] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ GMM
+// entropy_gmm_table_weight_kernel + _delta_kernel + _batch_forward_kernel + _check_kernel
+// (extension/entropy_gmm_table_cuda.cu:29-56, :83-105, :136-153) in one launch, one thread per symbol.
+// Expression shapes follow the reference's SASS: float v, FMUL s2*(v-mu), IEEE float division, erff,
+// DFMA(erf, .5, .5), DFMA(f, w, ps) rounded to float per component, FMUL total*ps, DADD .5, truncation.
+__global__ void gmm_table_kernel(float *__restrict__ logit, float *__restrict__ delta, const float *__restrict__ mean, int n,
+                                 int ng, int nstep, float bias, float total, float beta, float *__restrict__ cdf_f,
+                                 int *__restrict__ cdf_i)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    float w[PCX_MAX_GAUSS], d[PCX_MAX_GAUSS], mu[PCX_MAX_GAUSS];
+    float mval = -1e10f, psum = 0.f;
+    for (int i = 0; i < ng; i++) {
+        w[i] = logit[(i64)r * ng + i];
+        if (mval < w[i]) mval = w[i];
+    }
+    for (int i = 0; i < ng; i++) {
+        w[i] = exp(w[i] - mval);
+        psum += w[i];
+    }
+    for (int i = 0; i < ng; i++) {
+        w[i] = w[i] / psum;
+        logit[(i64)r * ng + i] = w[i];                  // in place, like the reference
+        float t = delta[(i64)r * ng + i];
+        t = t < 0 ? beta : t + beta;
+        delta[(i64)r * ng + i] = t;
+        d[i] = t;
+        mu[i] = mean[(i64)r * ng + i];
+    }
+    const float s2 = (float)(1. / sqrt(2.0));
+    float c[33];
+    c[0] = 0.f;
+    c[nstep] = (float)static_cast<int>(total);
+    for (int pt = 1; pt < nstep; pt++) {
+        float v = pt - 1 - bias + 0.5;
+        float ps = 0;
+        for (int i = 0; i < ng; i++) {
+            ps = ps + w[i] * (0.5 + 0.5 * erf(s2 * (v - mu[i]) / d[i]));
+        }
+        c[pt] = (float)static_cast<int>(total * ps + 0.5);
+    }
+    // strict-monotonic fix-up (:83-105), on integer-valued floats as the reference does
+    float fb = 0.f, mv = 0.f;
+    int midx = 0;
+    for (int i = 0; i < nstep; i++) {
+        if (c[i + 1] <= c[i]) fb += 1.f;
+        c[i + 1] += fb;
+        if (c[i + 1] - c[i] > mv) { mv = c[i + 1] - c[i]; midx = i; }
+    }
+    if (fb > 0.f)
+        for (int i = midx; i < nstep; i++) c[i + 1] -= fb;
+    for (int i = 0; i <= nstep; i++) {
+        if (cdf_f) cdf_f[(i64)r * (nstep + 1) + i] = c[i];
+        if (cdf_i) cdf_i[(i64)r * (nstep + 1) + i] = (int)c[i];
+    }
+}
+
+// entropy_gmm_forward_kernel (extension/entropy_gmm_cuda.cu:36-69), loss only
+__global__ void gmm_nll_kernel(const float *__restrict__ bottom_weight, const float *__restrict__ bottom_delta,
+                               const float *__restrict__ bottom_mean, const float *__restrict__ label, float *__restrict__ loss,
+                               int n, int ng)
+{
+    int index = blockIdx.x * blockDim.x + threadIdx.x;
+    if (index >= n) return;
+    float s2 = 1. / sqrt(float(2.0));
+    float sum_p = 0;
+    for (int i = 0; i < ng; i++) {
+        float xa = label[index] - 0.5 - bottom_mean[index * ng + i];
+        float xb = label[index] + 0.5 - bottom_mean[index * ng + i];
+        float id = 1. / bottom_delta[index * ng + i];
+        float fa = 0.5 + 0.5 * erf(xa * id * s2);
+        float fb = 0.5 + 0.5 * erf(xb * id * s2);
+        float p = fb - fa;
+        sum_p = sum_p + bottom_weight[index * ng + i] * p;
+    }
+    loss[index] = -log(sum_p + 0.0000001);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pcx_ctx_pad_step(float *d_buf, int nrep, int npart, int G, int cpn, int h, int W, int pad, int psum, const int *wl,
+                     const int *d_band, const int *d_row, const int *d_col, const float *d_tw, const int *d_items,
+                     const int *h_pstart, void *stream)
+{
+    Bands b;
+    PCX_REQUIRE(make_bands(b, wl, npart) == 0, "bad band description");
+    PCX_REQUIRE(d_buf && d_band && d_row && d_col && d_tw && d_items && h_pstart, "null pointer");
+    PCX_REQUIRE(nrep > 0 && G > 0 && cpn > 0 && h > 0 && W > 0 && pad > 0, "bad shape");
+    const int Hf = h * npart;
+    if (psum < 0 || psum >= Hf + W + pad + G - 2) return PCX_OK;          // :98
+    int st = psum - G + 1 < 0 ? 0 : psum - G + 1;
+    int en = psum < Hf + W + pad - 2 ? psum + 1 : Hf + W + pad - 1;
+    int nitems = h_pstart[en] - h_pstart[st];
+    if (nitems <= 0) return PCX_OK;
+    i64 total = (i64)nitems * cpn * nrep;
+    ctx_pad_kernel<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(d_buf, b, d_band, d_row, d_col, d_tw,
+                                                                           (const int4 *)d_items, h_pstart[st], nitems, nrep,
+                                                                           cpn, G * cpn, h, W, pad, psum);
+    PCX_LAUNCHED();
+    return PCX_OK;
+}
+
+int pcx_ctx_conv_step(const float *d_in, const float *d_weight, const float *d_bias, const float *d_act, float *d_out, int nb,
+                      int nimg, int npart, int G, int gi, int go, int h, int W, int pad_in, int pad_out, int constrain,
+                      int psum, const int *d_order, const int *h_start, void *stream)
+{
+    PCX_REQUIRE(d_in && d_weight && d_bias && d_out && d_order && h_start, "null pointer");
+    PCX_REQUIRE(nb > 0 && nimg > 0 && npart > 0 && G > 0 && go > 0 && h > 0 && W > 0, "bad shape");
+    PCX_REQUIRE(gi == 1 || gi == 3, "input channels per group must be 1 or 3 (got %d)", gi);
+    PCX_REQUIRE(constrain == 5 || constrain == 6, "constrain must be 5 or 6");
+    const int Hf = h * npart;
+    if (psum < 0 || psum >= Hf + W + G - 2) return PCX_OK;               // psum < mod_ (:398)
+    Window w = wave_window(h_start, psum, G, Hf, W);
+    if (w.count <= 0) return PCX_OK;
+    i64 nscalars = (i64)nb * nimg * go * w.count;
+    PCX_REQUIRE(nscalars < (1ll << 26), "wavefront too large");
+    const int threads = 256;
+    int blocks = grid_for(nscalars * 32, threads);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (gi == 1)
+        ctx_conv_kernel<1><<<blocks, threads, 0, s>>>(d_in, d_weight, d_bias, d_act, d_out, d_order, w.first, w.count, nimg,
+                                                      (int)nscalars, npart, G, go, h, W, pad_in, pad_out, constrain, psum);
+    else
+        ctx_conv_kernel<3><<<blocks, threads, 0, s>>>(d_in, d_weight, d_bias, d_act, d_out, d_order, w.first, w.count, nimg,
+                                                      (int)nscalars, npart, G, go, h, W, pad_in, pad_out, constrain, psum);
+    PCX_LAUNCHED();
+    return PCX_OK;
+}
+
+int pcx_ctx_add_step(float *d_y, const float *d_x, int nrep, int npart, int G, int cpg, int h, int W, int pad, int psum,
+                     const int *d_order, const int *h_start, void *stream)
+{
+    PCX_REQUIRE(d_y && d_x && d_order && h_start, "null pointer");
+    const int Hf = h * npart;
+    if (psum < 0 || psum > Hf + W + G - 2) return PCX_OK;                // psum <= mod_ (:56)
+    Window w = wave_window(h_start, psum, G, Hf, W);
+    i64 total = (i64)w.count * cpg * nrep;
+    if (total <= 0) return PCX_OK;
+    ctx_add_kernel<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(d_y, d_x, d_order, w.first, w.count, nrep, cpg, npart,
+                                                                           G * cpg, h, W, pad, psum);
+    PCX_LAUNCHED();
+    return PCX_OK;
+}
+
+int pcx_dinput_step(const float *d_sym, float *d_out, int nimg, int npart, int G, int h, int W, int pad, float bias, int rep,
+                    int psum, const int *d_order, const int *h_start, void *stream)
+{
+    PCX_REQUIRE(d_sym && d_out && d_order && h_start, "null pointer");
+    const int Hf = h * npart;
+    i64 rep_stride = (i64)nimg * npart * G * (h + 2 * pad) * (W + 2 * pad);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (psum == 0) {                                                       // :68-70
+        PCX_CUDA(cudaMemsetAsync(d_out, 0, sizeof(float) * rep * rep_stride, s));
+        return PCX_OK;
+    }
+    if (psum < 0 || psum > Hf + W + G - 2) return PCX_OK;
+    psum -= 1;
+    Window w = wave_window(h_start, psum, G, Hf, W);
+    i64 total = (i64)w.count * nimg;
+    if (total <= 0) return PCX_OK;
+    dinput_kernel<<<grid_for(total, 128), 128, 0, s>>>(d_sym, d_out, d_order, w.first, w.count, nimg, npart, G, h, W, pad, bias,
+                                                       rep, rep_stride, psum);
+    PCX_LAUNCHED();
+    return PCX_OK;
+}
+
+int pcx_dextract_step(const float *d_in, float *d_out, int nrep, int npart, int G, int cpn, int h, int W, int psum, int batch,
+                      int lag, const int *d_order, const int *h_start, int *h_count, void *stream)
+{
+    PCX_REQUIRE(d_in && d_out && d_order && h_start && h_count, "null pointer");
+    PCX_REQUIRE(!batch || nrep % 3 == 0, "batch extraction needs 3 nets");
+    const int Hf = h * npart;
+    const int mod = Hf + W + G - 2;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (lag) {                                                             // label_ == false branch (:85-98)
+        if (psum == 0) {
+            PCX_CUDA(cudaMemsetAsync(d_out, 0, sizeof(float) * (size_t)nrep * cpn * Hf * W, s));
+            return PCX_OK;
+        }
+        if (psum > mod) return PCX_OK;
+        psum -= 1;
+    } else if (psum >= mod) {
+        return PCX_OK;
+    }
+    Window w = wave_window(h_start, psum, G, Hf, W);
+    int nimg = batch ? nrep / 3 : nrep;
+    *h_count = nimg * w.count;
+    i64 total = (i64)w.count * cpn * nrep;
+    if (total <= 0) return PCX_OK;
+    dextract_kernel<<<grid_for(total, 128), 128, 0, s>>>(d_in, d_out, d_order, w.first, w.count, nrep, npart, G, cpn, h, W, psum,
+                                                         batch ? nimg : 0, (i64)cpn * Hf * W * nimg);
+    PCX_LAUNCHED();
+    return PCX_OK;
+}
+
+int pcx_gmm_table(float *d_logit, float *d_delta, const float *d_mean, int n, int ng, int nstep, float bias, float total,
+                  float beta, float *d_cdf_f, int *d_cdf_i, void *stream)
+{
+    PCX_REQUIRE(d_logit && d_delta && d_mean && (d_cdf_f || d_cdf_i), "null pointer");
+    PCX_REQUIRE(ng >= 1 && ng <= PCX_MAX_GAUSS, "num_gaussian %d > 16 (entropy_gmm_table_cuda.cu:13)", ng);
+    PCX_REQUIRE(nstep >= 2 && nstep <= 32, "nstep %d out of range", nstep);
+    if (n <= 0) return PCX_OK;                                             // tn > 0 (:163)
+    gmm_table_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(d_logit, d_delta, d_mean, n, ng, nstep, bias, total,
+                                                                         beta, d_cdf_f, d_cdf_i);
+    PCX_LAUNCHED();
+    return PCX_OK;
+}
+
+int pcx_gmm_nll(const float *d_w, const float *d_delta, const float *d_mean, const float *d_label, float *d_loss, int n,
+                int ng, void *stream)
+{
+    PCX_REQUIRE(d_w && d_delta && d_mean && d_label && d_loss, "null pointer");
+    PCX_REQUIRE(ng >= 1 && ng <= PCX_MAX_GAUSS, "num_gaussian %d out of range", ng);
+    if (n <= 0) return PCX_OK;
+    gmm_nll_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(d_w, d_delta, d_mean, d_label, d_loss, n, ng);
+    PCX_LAUNCHED();
+    return PCX_OK;
+}
+
+}  // extern "C"
