@@ -147,8 +147,10 @@ long long pcx_conv_pack_weights(const float *d_w, float *d_out, int Co, int Ci, 
  * pcx_gdn_params from the raw parameters (LowerBound, GDN.py:6-22). */
 int pcx_gdn_params(const float *d_beta, const float *d_gamma, float *d_beta_eff, float *d_gamma_eff,
                    int C, float beta_min, float reparam_offset, void *stream);
-int pcx_gdn_fwd(const float *d_x, const float *d_beta_eff, const float *d_gamma_eff, float *d_y,
-                int N, int C, int h, int W, int npart, const int *wl, int inverse, void *stream);
+/* d_residual (same shape as x, may be NULL): y = fill(residual + gdn(x)) - the block tail `trim(t + y)` of
+ * ResidualBlockDown / ResidualBlockUp (model_zoo_v2.py:107-114, :166-175) fused into the same pass. */
+int pcx_gdn_fwd(const float *d_x, const float *d_beta_eff, const float *d_gamma_eff, const float *d_residual,
+                float *d_y, int N, int C, int h, int W, int npart, const int *wl, int inverse, void *stream);
 
 /* ---- wavefront context model ------------------------------------------------------------------------
  * EntropyContextOp (main.cpp:55-59): entropy_context::reshape_hw (entropy_context_cuda.cu:13-45) builds the

@@ -123,8 +123,8 @@ constexpr int GTHREADS = 256; // 4 channel quarters x 64 pixels
 // gamma' is staged transposed in shared memory ([j][c], broadcast float4 reads), x^2 as [j][pixel].
 template <int C>
 __global__ void __launch_bounds__(GTHREADS) gdn_kernel(const float *__restrict__ x, const float *__restrict__ beta_eff,
-                                                       const float *__restrict__ gamma_eff, float *__restrict__ y, Bands bands,
-                                                       int h, int W, int inverse, i64 ntiles)
+                                                       const float *__restrict__ gamma_eff, const float *__restrict__ residual,
+                                                       float *__restrict__ y, Bands bands, int h, int W, int inverse, i64 ntiles)
 {
     extern __shared__ __align__(16) float sm[];
     float *gT = sm;                    // [C][C] : gT[j*C + c] = gamma'[c][j], loaded once per (persistent) CTA
@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(GTHREADS) gdn_kernel(const float *__restrict__
                 float v = xb[(i64)c * plane_stride + ox];
                 float nrm = sqrtf(acc[i]);
                 out = inverse ? __fmul_rn(v, nrm) : __fdiv_rn(v, nrm);
+                if (residual) out = __fadd_rn(residual[tile * C * plane_stride + (i64)row * W + (i64)c * plane_stride + ox], out);
             }
             yb[(i64)c * plane_stride + ox] = out;
         }
@@ -240,8 +241,8 @@ int pcx_gdn_params(const float *d_beta, const float *d_gamma, float *d_beta_eff,
     return PCX_OK;
 }
 
-int pcx_gdn_fwd(const float *d_x, const float *d_beta_eff, const float *d_gamma_eff, float *d_y, int N, int C, int h, int W,
-                int npart, const int *wl, int inverse, void *stream)
+int pcx_gdn_fwd(const float *d_x, const float *d_beta_eff, const float *d_gamma_eff, const float *d_residual, float *d_y, int N,
+                int C, int h, int W, int npart, const int *wl, int inverse, void *stream)
 {
     Bands b;
     PCX_REQUIRE(make_bands(b, wl, npart) == 0, "bad band description");
@@ -255,7 +256,7 @@ int pcx_gdn_fwd(const float *d_x, const float *d_beta_eff, const float *d_gamma_
         PCX_CUDA(cudaFuncSetAttribute(gdn_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    gdn_kernel<192><<<(unsigned)blocks, GTHREADS, smem, (cudaStream_t)stream>>>(d_x, d_beta_eff, d_gamma_eff, d_y, b, h, W, inverse, ntiles);
+    gdn_kernel<192><<<(unsigned)blocks, GTHREADS, smem, (cudaStream_t)stream>>>(d_x, d_beta_eff, d_gamma_eff, d_residual, d_y, b, h, W, inverse, ntiles);
     PCX_LAUNCHED();
     return PCX_OK;
 }

@@ -234,7 +234,6 @@ int pcx_halo_table(const int *wl, int npart, int h, int W, int pad, int mode, in
     Bands b;
     PCX_REQUIRE(make_bands(b, wl, npart) == 0, "bad band description");
     PCX_REQUIRE(h > 0 && W > 0 && pad > 0 && pad < 10, "bad halo geometry h=%d W=%d pad=%d (pad < 10: pseudo_context_cuda.cu:38)", h, W, pad);
-    PCX_REQUIRE(pad <= h, "pad %d larger than the band height %d", pad, h);
     PCX_REQUIRE(mode >= 0 && mode <= 2, "halo mode %d", mode);
     PCX_REQUIRE(d_band && d_row && d_col && d_tw, "null table pointer");
     i64 n = (i64)npart * 2 * pad * W;

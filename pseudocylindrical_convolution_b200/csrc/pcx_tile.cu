@@ -416,7 +416,7 @@ int launch_pad(const float *d_in, float *d_out, int N, int C, int h, int W, int 
     PCX_REQUIRE(make_bands(b, wl, npart) == 0, "bad band description");
     PCX_REQUIRE(d_in && d_out && d_band && d_row && d_col && d_tw, "null pointer");
     PCX_REQUIRE(N > 0 && C > 0 && h > 0 && W >= 4, "bad shape N=%d C=%d h=%d W=%d", N, C, h, W);
-    PCX_REQUIRE(pad > 0 && pad < 10 && pad <= h, "pad %d out of range (pseudo_context_cuda.cu:38)", pad);
+    PCX_REQUIRE(pad > 0 && pad < 10, "pad %d out of range (pseudo_context_cuda.cu:38)", pad);
     PCX_REQUIRE(C < 1000, "channel count %d >= 1000 (pseudo_context_cuda.cu:38)", C);
     PCX_REQUIRE(out_pitch >= W + 2 * pad, "out_pitch %d < %d", out_pitch, W + 2 * pad);
     PCX_REQUIRE(W <= 8192, "W=%d exceeds the 8192-column limit of the row pipeline", W);
@@ -482,7 +482,7 @@ int pcx_halo_fill(float *d_buf, int N, int C, int h, int W, int npart, int pad, 
     Bands b;
     PCX_REQUIRE(make_bands(b, wl, npart) == 0, "bad band description");
     PCX_REQUIRE(d_buf && d_band && d_row && d_col && d_tw, "null pointer");
-    PCX_REQUIRE(N > 0 && C > 0 && h > 0 && W > 0 && pad > 0 && pad <= h && pitch >= W + 2 * pad, "bad halo_fill geometry");
+    PCX_REQUIRE(N > 0 && C > 0 && h > 0 && W > 0 && pad > 0 && pitch >= W + 2 * pad, "bad halo_fill geometry");
     i64 planes = (i64)N * npart * C;
     i64 cells = planes * (2 * pad * (W + 2 * pad) + h * 2 * pad);
     int blocks = (int)((cells + 255) / 256 < (i64)pcx_sm_count() * 16 ? (cells + 255) / 256 : (i64)pcx_sm_count() * 16);
