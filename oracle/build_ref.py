@@ -36,6 +36,11 @@ def build(which=("coder", "pconv"), verbose=False):
         print(f"[build_ref] {REF} not present - keeping whatever is prebuilt in {OUT}")
         return False
     os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
+    # this image exports CXX=/opt/gcc/bin/g++, a wrapper that links libstdc++ STATICALLY; a private libstdc++ inside
+    # a Python extension crashes in std::stringstream (uninitialised locale) - use the system compiler instead
+    for var, exe in (("CXX", "/usr/bin/g++"), ("CC", "/usr/bin/gcc")):
+        if os.path.exists(exe):
+            os.environ[var] = exe
     os.environ.setdefault("MAX_JOBS", str(os.cpu_count() or 4))
     from torch.utils import cpp_extension as ce
     os.makedirs(OUT, exist_ok=True)

@@ -136,8 +136,20 @@ API void orc_uslice_table(const int *wl, int npart, int W, int *src, float *wt)
         }
 }
 
-/* 4-tap accumulate, strict left to right: FMUL then three FFMA (sphere_slice_cuda.cu:109-113). */
-static inline float tap4(const float *w, float a, float b, float c, float d)
+/* 4-tap accumulate.  nvcc chooses which product is the plain FMUL and chooses differently in the two kernels
+ * (verified on the reference's SASS, nvcc 12.9 sm_100):
+ *   slice  (sphere_slice_cuda.cu:109-113): FMUL p2*i2, then FFMA p1*i1, p3*i3, p4*i4
+ *   uslice (sphere_uslice_cuda.cu:91-96) : FMUL p1*i1, then FFMA p2*i2, p3*i3, p4*i4 */
+static inline float tap4_slice(const float *w, float a, float b, float c, float d)
+{
+    float r = w[1] * b;
+    r = fmaf(w[0], a, r);
+    r = fmaf(w[2], c, r);
+    r = fmaf(w[3], d, r);
+    return r;
+}
+
+static inline float tap4_uslice(const float *w, float a, float b, float c, float d)
 {
     float r = w[0] * a;
     r = fmaf(w[1], b, r);
@@ -163,7 +175,7 @@ API void orc_slice(const float *in, float *out, int N, int C, int H, int W, int 
                         if (x >= wl[g]) { o[x] = 0.f; continue; }
                         i64 k = (i64)g * W + x;
                         int p = src[k];
-                        o[x] = tap4(wt + k * 4, row[(p - 1 + W) % W], row[p], row[(p + 1) % W], row[(p + 2) % W]);
+                        o[x] = tap4_slice(wt + k * 4, row[(p - 1 + W) % W], row[p], row[(p + 1) % W], row[(p + 2) % W]);
                     }
                 }
 }
@@ -183,7 +195,7 @@ API void orc_uslice(const float *in, float *out, int N, int C, int h, int W, int
                     for (int x = 0; x < W; x++) {
                         i64 k = (i64)g * W + x;
                         int p = src[k];
-                        o[x] = tap4(wt + k * 4, row[(p - 1 + w) % w], row[p], row[(p + 1) % w], row[(p + 2) % w]);
+                        o[x] = tap4_uslice(wt + k * 4, row[(p - 1 + w) % w], row[p], row[(p + 1) % w], row[(p + 2) % w]);
                     }
                 }
 }

@@ -122,11 +122,21 @@ __device__ __forceinline__ float lerp2_ref(float a, float b, float t)
     r = __fmul_rn(b, r);
     return __fmaf_rn(a, t, r);
 }
-// 4-tap cubic in the reference's compiled shape (sphere_slice_cuda.cu:109-113): FMUL + 3 chained FFMA
+// 4-tap cubic in the reference's compiled shapes.  nvcc picks which product of p1*i1 + p2*i2 + p3*i3 + p4*i4 is
+// the plain FMUL (the rest are chained FFMAs), and it picks differently in the two kernels (SASS, nvcc 12.9):
+//   sphere_slice_forward_kernel  (sphere_slice_cuda.cu:109-113): FMUL p2*i2, FFMA p1*i1, FFMA p3*i3, FFMA p4*i4
+//   sphere_uslice_forward_kernel (sphere_uslice_cuda.cu:91-96) : FMUL p1*i1, FFMA p2*i2, FFMA p3*i3, FFMA p4*i4
+template <bool SLICE_ORDER>
 __device__ __forceinline__ float tap4_ref(float4 w, float a, float b, float c, float d)
 {
-    float r = __fmul_rn(w.x, a);
-    r = __fmaf_rn(w.y, b, r);
+    float r;
+    if (SLICE_ORDER) {
+        r = __fmul_rn(w.y, b);
+        r = __fmaf_rn(w.x, a, r);
+    } else {
+        r = __fmul_rn(w.x, a);
+        r = __fmaf_rn(w.y, b, r);
+    }
     r = __fmaf_rn(w.z, c, r);
     r = __fmaf_rn(w.w, d, r);
     return r;

@@ -1,16 +1,515 @@
-// pcx_conv_tc.cu - tcgen05 / TMEM implicit-GEMM convolution (TF32 operands, fp32 accumulate).
+// pcx_conv_tc.cu - pseudocylindrical convolution as an implicit GEMM on the 5th-generation tensor cores.
+//
+//   D[pixel, co] = sum over taps (ky,kx) and input channels ci of  X[ci, y*s+ky, x*s+kx] * W[co, ci, ky, kx]
+//
+// Mapping (one CTA per SM, persistent over output tiles):
+//   M = 128 output pixels  = 4 chunks of 32 consecutive pixels of one output row (CX chunks per row, 4/CX rows)
+//   N = NT output channels = 16 / 96 / 192 per tile (768-channel layers run as 4 N-tiles)
+//   K = taps x Ci, streamed in blocks of 32 input channels of one tap
+//   A operand: straight from the padded NCHW activation tensor.  Pixels are contiguous in memory, channels are
+//      strided, i.e. A is "MN-major": one TMA box (32 pixels x 32 channels, SWIZZLE_128B) per chunk lands as four
+//      1024-byte UMMA atoms (32 pixels x 8 channels each); descriptor LBO = chunk stride, SBO = 1024.  A tap is
+//      just a coordinate offset of the box, so the halo-padded tile layout needs no im2col.
+//   B operand: weights repacked once to [tap][Co_pad][Ci] (K-major, SWIZZLE_128B), one TMA box NT x 32 per block.
+//   D: fp32 accumulator in TMEM, 2 stages (2 x NT columns) so the epilogue of tile i overlaps the MMAs of i+1.
+//   tcgen05.mma.cta_group::1.kind::tf32, M=128, N=NT, K=8: four per K block, issued by one elected thread.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2..5 epilogue (TMEM -> registers ->
+// bias, PReLU / sigmoid, gate, residual, invalid-column zeroing -> coalesced NCHW stores; lane = pixel).
 #include "pcx_common.cuh"
+#include <cuda.h>
+#include <mutex>
 
-int pcx_conv2d_tc(const pcx_conv_desc *d, const float *d_x, const float *d_w, const float *d_bias, const float *d_slope,
-                  const float *d_mul, const float *d_residual, float *d_y, void *stream)
+namespace {
+
+constexpr int BLOCK_M = 128;          // pixels per tile
+constexpr int CHUNK = 32;             // pixels per TMA box / per epilogue warp
+constexpr int BLOCK_K = 32;           // input channels per pipeline stage
+constexpr int UMMA_K = 8;             // tf32
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;     // 16 KB: 4 chunks x (32 ch x 128 B)
+constexpr int A_CHUNK_BYTES = CHUNK * BLOCK_K * 4;       // 4 KB
+constexpr int NUM_THREADS = 192;      // 6 warps
+constexpr int EPI_WARP0 = 2;
+
+struct TcParams {
+    int planes, npart;
+    int Ci, Co, Ho, Wo;
+    int out_rows, out_pitch, out_y0, out_x0;
+    int aux_rows, aux_pitch, aux_y0, aux_x0;
+    int k, stride, act;
+    int cx;                 // chunks per output row inside a tile (1, 2 or 4)
+    int tiles_x, tiles_y, n_tiles, co_pad;
+    long long total_tiles;
+    int wl_out[PCX_MAX_PART];
+};
+
+template <int NT>
+struct Cfg {
+    static constexpr int B_STAGE_BYTES = NT * BLOCK_K * 4;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int TMEM_COLS = NT * 2 <= 32 ? 32 : (NT * 2 <= 64 ? 64 : (NT * 2 <= 128 ? 128 : (NT * 2 <= 256 ? 256 : 512)));
+    static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ bool elect_one()
 {
-    (void)d; (void)d_x; (void)d_w; (void)d_bias; (void)d_slope; (void)d_mul; (void)d_residual; (void)d_y; (void)stream;
-    pcx_set_error("tensor-core convolution is not built into this libpcx");
-    return PCX_EINVAL;
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, 0xffffffff;\n"
+        "@px mov.s32 %0, 1;\n"
+        "}\n"
+        : "+r"(pred));
+    return pred != 0;
 }
+
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 operands, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) [4,6), a/b format TF32 (2) [7,10) [10,13),
+// a_major MN (1) [15], b_major K (0) [16], N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t instr_desc(int n)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+struct Tile {
+    long long plane;
+    int y0, x0, n0;
+};
+
+__device__ __forceinline__ Tile decode_tile(const TcParams &p, long long t)
+{
+    Tile r;
+    r.n0 = (int)(t % p.n_tiles); t /= p.n_tiles;
+    r.x0 = (int)(t % p.tiles_x) * (CHUNK * p.cx); t /= p.tiles_x;
+    r.y0 = (int)(t % p.tiles_y) * (4 / p.cx); t /= p.tiles_y;
+    r.plane = t;
+    return r;
+}
+
+// a tile does tensor-core work only if it holds at least one valid pixel of its band
+__device__ __forceinline__ bool tile_live(const TcParams &p, const Tile &t)
+{
+    return t.x0 < p.wl_out[(int)(t.plane % p.npart)];
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                                  const __grid_constant__ CUtensorMap map_w, TcParams p,
+                                                                  const float *__restrict__ bias, const float *__restrict__ slope,
+                                                                  const float *__restrict__ mul, const float *__restrict__ residual,
+                                                                  float *__restrict__ y)
+{
+    using C = Cfg<NT>;
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B operands need 1024-byte alignment
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *stage_base = smem;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + C::STAGES;
+    uint64_t *acc_full = empty_bar + C::STAGES;     // [2]
+    uint64_t *acc_empty = acc_full + 2;             // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_x);
+        prefetch_tmap(&map_w);
+        for (int s = 0; s < C::STAGES; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], 4);           // one arrival per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int taps = p.k * p.k;
+    const int kblocks = p.Ci / BLOCK_K;
+    const int iters = taps * kblocks;
+
+    if (warp == 0) {
+        // ===================================================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                Tile tl = decode_tile(p, t);
+                if (!tile_live(p, tl)) continue;
+                for (int it = 0; it < iters; it++) {
+                    const int tap = it / kblocks, kb = it % kblocks;
+                    const int ky = tap / p.k, kx = tap % p.k;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char *sa = stage_base + (size_t)stage * C::STAGE_BYTES;
+                    unsigned char *sb = sa + A_STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const int oy = tl.y0 + c / p.cx, ox = tl.x0 + (c % p.cx) * CHUNK;
+                        tma_load_4d(sa + c * A_CHUNK_BYTES, &map_x, &full_bar[stage], ox * p.stride + kx, oy * p.stride + ky,
+                                    kb * BLOCK_K, (int)tl.plane);
+                    }
+                    tma_load_3d(sb, &map_w, &full_bar[stage], kb * BLOCK_K, tl.n0 * NT, tap);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================================== MMA issuer
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        constexpr uint32_t idesc = instr_desc(NT);
+        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            Tile tl = decode_tile(p, t);
+            if (!tile_live(p, tl)) continue;
+            mbar_wait(&acc_empty[acc], acc_phase ^ 1);        // epilogue has drained this accumulator stage
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * NT;
+            for (int it = 0; it < iters; it++) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {          // one thread issues the MMAs and, below, the commits that track them
+                    const uint32_t sa = smem_u32(stage_base + (size_t)stage * C::STAGE_BYTES);
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < BLOCK_K / UMMA_K; kk++) {
+                        // A (MN-major): K atom kk starts 1024 B further; chunks (M) are A_CHUNK_BYTES apart
+                        const uint64_t ad = smem_desc(sa + kk * 1024, A_CHUNK_BYTES, 1024);
+                        // B (K-major): 8 tf32 = 32 B further inside the 128 B row; 8-row groups 1024 B apart
+                        const uint64_t bd = smem_desc(sb + kk * UMMA_K * 4, 16, 1024);
+                        umma_tf32(tmem_d, ad, bd, idesc, (it | kk) != 0);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) umma_commit(&empty_bar[stage]);      // smem slot free once these MMAs are done
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (lane == 0) umma_commit(&acc_full[acc]);             // accumulator complete -> epilogue
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ===================================================================================== epilogue warps
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may read = chunk index
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            Tile tl = decode_tile(p, t);
+            const int g = (int)(tl.plane % p.npart);
+            const int wl = p.wl_out[g];
+            const int oy = tl.y0 + q / p.cx;
+            const int ox = tl.x0 + (q % p.cx) * CHUNK + lane;
+            const bool in_plane = oy < p.Ho && ox < p.Wo;
+            const bool valid = in_plane && ox < wl;
+            const bool live = tile_live(p, tl);
+            if (live) {
+                mbar_wait(&acc_full[acc], acc_phase);
+                tc_fence_after();
+            }
+            const int nco = min(NT, p.Co - tl.n0 * NT);
+            float *yp = y + ((tl.plane * p.Co + (long long)tl.n0 * NT) * p.out_rows + oy + p.out_y0) * (long long)p.out_pitch + ox + p.out_x0;
+            const long long ystride = (long long)p.out_rows * p.out_pitch;
+            const long long aoff = ((tl.plane * p.Co + (long long)tl.n0 * NT) * p.aux_rows + oy + p.aux_y0) * (long long)p.aux_pitch + ox + p.aux_x0;
+            const long long astride = (long long)p.aux_rows * p.aux_pitch;
+            constexpr int STEP = NT >= 32 ? 32 : 16;
+#pragma unroll 1
+            for (int c0 = 0; c0 < NT; c0 += STEP) {
+                uint32_t v[STEP];
+                if (live) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + c0);
+                    if constexpr (STEP == 32) tmem_ld32(taddr, v);
+                    else tmem_ld16(taddr, v);
+                    tmem_wait_ld();
+                }
+                if (in_plane) {
+#pragma unroll
+                    for (int j = 0; j < STEP; j++) {
+                        const int co = c0 + j;
+                        if (co >= nco) break;
+                        float r = 0.f;
+                        if (valid) {
+                            const int cg = tl.n0 * NT + co;
+                            r = __uint_as_float(v[j]);
+                            if (bias) r = __fadd_rn(r, __ldg(bias + cg));
+                            if (p.act == 1) { if (r < 0.f) r = __fmul_rn(r, __ldg(slope + cg)); }
+                            else if (p.act == 2) r = 1.0f / (1.0f + expf(-r));
+                            if (mul) r = __fmul_rn(r, __ldg(mul + aoff + co * astride));
+                            if (residual) r = __fadd_rn(__ldg(residual + aoff + co * astride), r);
+                        }
+                        yp[co * ystride] = r;
+                    }
+                }
+            }
+            if (live) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// OIHW fp32 -> [tap][Co_pad][Ci], values rounded to the nearest TF32 (the MMA would otherwise truncate them)
+__global__ void pack_weights_kernel(const float *__restrict__ w, float *__restrict__ out, int Co, int Ci, int kk, int co_pad)
+{
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)kk * co_pad * Ci;
+    if (idx >= total) return;
+    int ci = (int)(idx % Ci);
+    int co = (int)((idx / Ci) % co_pad);
+    int tap = (int)(idx / Ci / co_pad);
+    float v = 0.f;
+    if (co < Co) {
+        v = w[((long long)co * Ci + ci) * kk + tap];
+        uint32_t r;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+        v = __uint_as_float(r);
+    }
+    out[idx] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    });
+    return fn;
+}
+
+int n_tile_for(int Co) { return Co <= 16 ? 16 : (Co % 192 == 0 ? 192 : (Co % 96 == 0 ? 96 : 0)); }
+
+struct PackedWeights {
+    const float *src = nullptr;
+    float *dst = nullptr;
+    int Co = 0, Ci = 0, k = 0, co_pad = 0;
+    unsigned long long stamp = 0;
+};
+
+}  // namespace
+
+// Weight repacking is cached per (pointer, shape, content stamp); the stamp is the caller's version counter.
+static std::mutex g_pack_mutex;
+static PackedWeights g_pack_cache[512];
+static int g_pack_next = 0;
 
 extern "C" long long pcx_conv_pack_weights(const float *d_w, float *d_out, int Co, int Ci, int k, void *stream)
 {
-    (void)d_w; (void)d_out; (void)stream;
-    return (long long)k * k * Co * Ci;
+    int nt = n_tile_for(Co);
+    if (nt == 0 || Ci % BLOCK_K != 0 || (k != 1 && k != 3)) {
+        pcx_set_error("tensor-core conv supports Co <= 16 or a multiple of 96, Ci a multiple of 32, k in {1,3} (got Co=%d Ci=%d k=%d)", Co, Ci, k);
+        return PCX_EINVAL;
+    }
+    int co_pad = (Co + nt - 1) / nt * nt;
+    long long total = (long long)k * k * co_pad * Ci;
+    if (d_out == nullptr) return total;
+    if (d_w == nullptr) { pcx_set_error("null weights"); return PCX_EINVAL; }
+    pack_weights_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(d_w, d_out, Co, Ci, k * k, co_pad);
+    PCX_LAUNCHED();
+    return total;
+}
+
+template <int NT>
+static int launch_tc(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, const float *bias, const float *slope,
+                     const float *mul, const float *residual, float *y, cudaStream_t s)
+{
+    using C = Cfg<NT>;
+    static bool attr = false;
+    if (!attr) {
+        PCX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        attr = true;
+    }
+    long long grid = p.total_tiles < pcx_sm_count() ? p.total_tiles : pcx_sm_count();
+    conv_tc_kernel<NT><<<(unsigned)grid, NUM_THREADS, C::SMEM, s>>>(mx, mw, p, bias, slope, mul, residual, y);
+    PCX_LAUNCHED();
+    return PCX_OK;
+}
+
+int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w, const float *d_bias, const float *d_slope,
+                  const float *d_mul, const float *d_residual, float *d_y, void *stream)
+{
+    const pcx_conv_desc &d = *desc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nt = n_tile_for(d.Co);
+    PCX_REQUIRE(nt != 0 && d.Ci % BLOCK_K == 0, "tensor-core conv needs Co <= 16 or a multiple of 96 and Ci a multiple of 32 (Co=%d Ci=%d); use impl=1", d.Co, d.Ci);
+    PCX_REQUIRE(d.in_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15) == 0, "TMA needs a 16-byte aligned input with a pitch that is a multiple of 4 floats (pitch=%d); use impl=1", d.in_pitch);
+    EncodeTiledFn enc = encode_tiled();
+    PCX_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+
+    // ---- weights: repack once per (pointer, shape); d_w is the caller's OIHW tensor
+    const int co_pad = (d.Co + nt - 1) / nt * nt;
+    float *packed = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_pack_mutex);
+        for (auto &e : g_pack_cache)
+            if (e.src == d_w && e.Co == d.Co && e.Ci == d.Ci && e.k == d.k) { packed = e.dst; break; }
+        if (!packed) {
+            PackedWeights &e = g_pack_cache[g_pack_next];
+            g_pack_next = (g_pack_next + 1) % 512;
+            if (e.dst) cudaFree(e.dst);
+            size_t n = (size_t)d.k * d.k * co_pad * d.Ci;
+            PCX_CUDA(cudaMalloc(&e.dst, n * sizeof(float)));
+            e.src = d_w; e.Co = d.Co; e.Ci = d.Ci; e.k = d.k; e.co_pad = co_pad;
+            packed = e.dst;
+        }
+    }
+    // weights may have been updated in place (load_state_dict): repacking is cheap (<= 5 MB), do it every call
+    long long rc = pcx_conv_pack_weights(d_w, packed, d.Co, d.Ci, d.k, stream);
+    if (rc < 0) return (int)rc;
+
+    // ---- tensor maps
+    CUtensorMap mx, mw;
+    {
+        const long long planes = (long long)d.N * d.npart;
+        cuuint64_t dims[4] = {(cuuint64_t)d.in_pitch, (cuuint64_t)d.Hi, (cuuint64_t)d.Ci, (cuuint64_t)planes};
+        cuuint64_t strides[3] = {(cuuint64_t)d.in_pitch * 4, (cuuint64_t)d.in_pitch * d.Hi * 4, (cuuint64_t)d.in_pitch * d.Hi * d.Ci * 4};
+        cuuint32_t box[4] = {(cuuint32_t)(CHUNK * d.stride), 1, BLOCK_K, 1};
+        cuuint32_t estr[4] = {(cuuint32_t)d.stride, 1, 1, 1};
+        CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(d_x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        PCX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activations) failed with %d", (int)r);
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)d.Ci, (cuuint64_t)co_pad, (cuuint64_t)(d.k * d.k)};
+        cuuint64_t strides[2] = {(cuuint64_t)d.Ci * 4, (cuuint64_t)d.Ci * co_pad * 4};
+        cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)nt, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, packed, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        PCX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+    }
+
+    TcParams p;
+    p.planes = d.N * d.npart; p.npart = d.npart;
+    p.Ci = d.Ci; p.Co = d.Co; p.Ho = d.Ho; p.Wo = d.Wo;
+    p.out_rows = d.out_rows; p.out_pitch = d.out_pitch; p.out_y0 = d.out_y0; p.out_x0 = d.out_x0;
+    p.aux_rows = d.aux_rows; p.aux_pitch = d.aux_pitch; p.aux_y0 = d.aux_y0; p.aux_x0 = d.aux_x0;
+    p.k = d.k; p.stride = d.stride; p.act = d.act;
+    p.cx = d.Wo >= 128 ? 4 : (d.Wo >= 64 ? 2 : 1);
+    p.tiles_x = (d.Wo + CHUNK * p.cx - 1) / (CHUNK * p.cx);
+    p.tiles_y = (d.Ho + (4 / p.cx) - 1) / (4 / p.cx);
+    p.n_tiles = co_pad / nt;
+    p.co_pad = co_pad;
+    p.total_tiles = (long long)p.planes * p.tiles_y * p.tiles_x * p.n_tiles;
+    for (int i = 0; i < PCX_MAX_PART; i++) p.wl_out[i] = d.wl_out[i];
+
+    if (nt == 192) return launch_tc<192>(mx, mw, p, d_bias, d_slope, d_mul, d_residual, d_y, s);
+    if (nt == 96) return launch_tc<96>(mx, mw, p, d_bias, d_slope, d_mul, d_residual, d_y, s);
+    return launch_tc<16>(mx, mw, p, d_bias, d_slope, d_mul, d_residual, d_y, s);
 }

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(MAXT) resample_rows_kernel(const float *__rest
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 int p = tap[ch][j];
-                v[j] = (p < 0) ? 0.f : tap4_ref(wt[ch][j], row[p - 1], row[p], row[p + 1], row[p + 2]);
+                v[j] = (p < 0) ? 0.f : tap4_ref<TO_TILES>(wt[ch][j], row[p - 1], row[p], row[p + 1], row[p + 2]);
             }
             if (vec_store) {
                 st_cs_f4(dst + x0, make_float4(v[0], v[1], v[2], v[3]));
