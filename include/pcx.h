@@ -120,8 +120,10 @@ int pcx_dquant_fwd(const float *d_sym, const float *d_theta, float *d_centres, f
  * (so a layer can write straight into the interior of the next layer's padded buffer).
  * Epilogue, in this order:  +bias ; act ; +residual ; zero columns >= wl_out[band] (PseudoFillV2).
  *   act: 0 none, 1 PReLU(d_slope per channel), 2 sigmoid.
- * impl: 0 = tcgen05/TMEM implicit GEMM (TF32 operands, fp32 accumulate), 1 = fp32 CUDA-core direct form
- *       (exact-order reference used to validate impl 0 on the device). */
+ * impl: 0 = tcgen05/TMEM implicit GEMM (TF32 operands, fp32 accumulate); tensors are NHWC
+ *           (x [plane][Hi][in_pitch][Ci], y [plane][out_rows][out_pitch][Co], aux likewise), Ci % 32 == 0,
+ *           Co <= 16 or Co % 96 == 0;
+ *       1 = fp32 CUDA-core direct form on NCHW tensors (exact-order reference used to validate impl 0). */
 typedef struct pcx_conv_desc {
     int N, npart;            /* images, bands per image */
     int Ci, Hi, in_pitch;    /* input planes: Hi rows of in_pitch floats */
@@ -191,8 +193,10 @@ int pcx_dextract_step(const float *d_in, float *d_out, int nrep, int npart, int 
  * EntropyGmmTableOp.forward_batch / forward (main.cpp:49-53 -> entropy_gmm_table_cuda.cu:107-185).
  * Softmax and delta clamp are applied IN PLACE on the inputs like the reference; d_cdf_f (n, nstep+1) fp32
  * integer-valued table (reference layout) and/or d_cdf_i int32 (what the coder consumes); either may be NULL. */
+/* form 0 = arithmetic of entropy_gmm_table_batch_forward_kernel (:136-153, what the codec uses),
+ * form 1 = entropy_gmm_table_forward_kernel (:59-80): the two reference kernels round differently. */
 int pcx_gmm_table(float *d_logit, float *d_delta, const float *d_mean, int n, int ng, int nstep, float bias,
-                  float total, float beta, float *d_cdf_f, int *d_cdf_i, void *stream);
+                  float total, float beta, int form, float *d_cdf_f, int *d_cdf_i, void *stream);
 /* EntropyGmmOp.forward (main.cpp:24-28 -> entropy_gmm_cuda.cu:72-92): loss only. */
 int pcx_gmm_nll(const float *d_w, const float *d_delta, const float *d_mean, const float *d_label,
                 float *d_loss, int n, int ng, void *stream);

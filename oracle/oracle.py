@@ -325,7 +325,7 @@ def dextract_step(x, out, geom, G, psum, batch):
                                    int(psum), 1 if batch else 0, _ip(geom.order), _ip(geom.start))
 
 
-def gmm_table(logit, delta, mean, nstep=8, bias=3.5, total=65536.0, beta=1e-6):
+def gmm_table(logit, delta, mean, nstep=8, bias=3.5, total=65536.0, beta=1e-6, form=0):
     """entropy_gmm_table_cuda.cu:29-56, :83-105, :136-153 -> int32 (n, nstep+1)."""
     logit, lp = _f(logit)
     delta, dp = _f(delta)
@@ -334,7 +334,7 @@ def gmm_table(logit, delta, mean, nstep=8, bias=3.5, total=65536.0, beta=1e-6):
     cdf = np.zeros((n, nstep + 1), np.int32)
     w = np.zeros_like(logit)
     d = np.zeros_like(logit)
-    lib().orc_gmm_table(lp, dp, mp, n, ng, int(nstep), C.c_float(bias), C.c_float(total), C.c_float(beta),
+    lib().orc_gmm_table(lp, dp, mp, n, ng, int(nstep), C.c_float(bias), C.c_float(total), C.c_float(beta), int(form),
                         _ip(cdf), _fp(w), _fp(d))
     return cdf, w, d
 

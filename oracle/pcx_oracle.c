@@ -684,7 +684,7 @@ API int orc_dextract_step(const float *in, float *out, int nrep, int npart, int 
  * differs by <= 1-2 ulp, so cdf entries may differ from the GPU by +-1 on rare rows.
  * ---------------------------------------------------------------------------------------------- */
 API void orc_gmm_table(const float *logit, const float *delta, const float *mean, int n, int ng,
-                       int nstep, float bias, float total, float beta, int *cdf,
+                       int nstep, float bias, float total, float beta, int form, int *cdf,
                        float *w_out, float *d_out)
 {
     float s2 = (float)(1. / sqrt(2.0));
@@ -706,7 +706,8 @@ API void orc_gmm_table(const float *logit, const float *delta, const float *mean
             for (int i = 0; i < ng; i++) {
                 float z = s2 * (v - mean[r * ng + i]) / d[i];
                 double f = fma(0.5, (double)erff(z), 0.5);
-                ps = (float)fma(f, (double)w[i], (double)ps);
+                if (form == 0) ps = (float)fma(f, (double)w[i], (double)ps);   /* batch kernel :146-150: DFMA, one rounding */
+                else ps = fmaf((float)f, w[i], ps);                            /* plain kernel :69-72: f stored to float, FFMA */
             }
             c[pt] = (float)(int)((double)(total * ps) + 0.5);
         }

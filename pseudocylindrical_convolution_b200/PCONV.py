@@ -608,7 +608,7 @@ class EntropyGmmTableOp(_Op):
         with torch.cuda.device(weight.device):
             out = self._out("top", (rows, self.nstep_ + 1), weight)
             call("pcx_gmm_table", _p(weight), _p(delta), _p(mean), tn, self.num_gaussian_, self.nstep_, C.c_float(self.bias_),
-                 C.c_float(self.total_region_), C.c_float(self.beta_), _p(out), None, _stream())
+                 C.c_float(self.total_region_), C.c_float(self.beta_), 1, _p(out), None, _stream())
         return [out]
 
     def forward_batch(self, data, tnum):
@@ -622,7 +622,7 @@ class EntropyGmmTableOp(_Op):
             flat = data.view(-1)
             call("pcx_gmm_table", _p(flat), C.c_void_p(flat.data_ptr() + 4 * stride), C.c_void_p(flat.data_ptr() + 8 * stride),
                  tn, self.num_gaussian_, self.nstep_, C.c_float(self.bias_), C.c_float(self.total_region_),
-                 C.c_float(self.beta_), _p(out), None, _stream())
+                 C.c_float(self.beta_), 0, _p(out), None, _stream())
         return [out]
 
 

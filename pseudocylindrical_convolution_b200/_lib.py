@@ -60,7 +60,7 @@ PROTOTYPES = {
     "pcx_ctx_add_step": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _IP, _P]),
     "pcx_dinput_step": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _IP, _P]),
     "pcx_dextract_step": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _IP, _IP, _P]),
-    "pcx_gmm_table": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _P, _P, _P]),
+    "pcx_gmm_table": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _I, _P, _P, _P]),
     "pcx_gmm_nll": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "pcx_coder_open": (_P, [C.c_char_p]),
     "pcx_coder_close": (None, [_P]),

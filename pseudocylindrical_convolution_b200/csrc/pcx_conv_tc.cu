@@ -1,20 +1,21 @@
 // pcx_conv_tc.cu - pseudocylindrical convolution as an implicit GEMM on the 5th-generation tensor cores.
 //
-//   D[pixel, co] = sum over taps (ky,kx) and input channels ci of  X[ci, y*s+ky, x*s+kx] * W[co, ci, ky, kx]
+//   D[pixel, co] = sum over taps (ky,kx) and input channels ci of  X[y*s+ky, x*s+kx, ci] * W[co, ci, ky, kx]
 //
-// Mapping (one CTA per SM, persistent over output tiles):
-//   M = 128 output pixels  = 4 chunks of 32 consecutive pixels of one output row (CX chunks per row, 4/CX rows)
+// Activations are NHWC ("tile-major, channels last": [plane][row][column][channel]) so that a filter tap is a
+// coordinate offset in the two OUTER dimensions of the TMA tensor map - TMA cannot start a box at an
+// unaligned innermost coordinate (measured: illegal instruction), which rules out walking taps along a
+// contiguous pixel axis.  Mapping (one CTA per SM, persistent over output tiles):
+//   M = 128 output pixels  = bw columns x bh rows of one plane (bw*bh = 128, bw in {128, 64, 32})
 //   N = NT output channels = 16 / 96 / 192 per tile (768-channel layers run as 4 N-tiles)
 //   K = taps x Ci, streamed in blocks of 32 input channels of one tap
-//   A operand: straight from the padded NCHW activation tensor.  Pixels are contiguous in memory, channels are
-//      strided, i.e. A is "MN-major": one TMA box (32 pixels x 32 channels, SWIZZLE_128B) per chunk lands as four
-//      1024-byte UMMA atoms (32 pixels x 8 channels each); descriptor LBO = chunk stride, SBO = 1024.  A tap is
-//      just a coordinate offset of the box, so the halo-padded tile layout needs no im2col.
+//   A operand: ONE TMA box (32 channels x bw x bh, SWIZZLE_128B) per K block straight from the halo-padded
+//      activation buffer - 128 rows of 128 bytes, K-major; stride-2 layers use the tensor map's element strides.
 //   B operand: weights repacked once to [tap][Co_pad][Ci] (K-major, SWIZZLE_128B), one TMA box NT x 32 per block.
 //   D: fp32 accumulator in TMEM, 2 stages (2 x NT columns) so the epilogue of tile i overlaps the MMAs of i+1.
-//   tcgen05.mma.cta_group::1.kind::tf32, M=128, N=NT, K=8: four per K block, issued by one elected thread.
+//   tcgen05.mma.cta_group::1.kind::tf32, M=128, N=NT, K=8: four per K block, issued by one thread.
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2..5 epilogue (TMEM -> registers ->
-// bias, PReLU / sigmoid, gate, residual, invalid-column zeroing -> coalesced NCHW stores; lane = pixel).
+// bias, PReLU / sigmoid, gate, residual, invalid-column zeroing -> 128-bit NHWC stores; lane = pixel).
 #include "pcx_common.cuh"
 #include <cuda.h>
 #include <mutex>
@@ -22,13 +23,10 @@
 namespace {
 
 constexpr int BLOCK_M = 128;          // pixels per tile
-constexpr int CHUNK = 32;             // pixels per TMA box / per epilogue warp
-constexpr int BLOCK_K = 32;           // input channels per pipeline stage
+constexpr int BLOCK_K = 32;           // input channels per pipeline stage (= one 128-byte swizzled row)
 constexpr int UMMA_K = 8;             // tf32
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;     // 16 KB: 4 chunks x (32 ch x 128 B)
-constexpr int A_CHUNK_BYTES = CHUNK * BLOCK_K * 4;       // 4 KB
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;     // 16 KB: 128 pixel rows x 128 B
 constexpr int NUM_THREADS = 192;      // 6 warps
-constexpr int EPI_WARP0 = 2;
 
 struct TcParams {
     int planes, npart;
@@ -36,7 +34,7 @@ struct TcParams {
     int out_rows, out_pitch, out_y0, out_x0;
     int aux_rows, aux_pitch, aux_y0, aux_x0;
     int k, stride, act;
-    int cx;                 // chunks per output row inside a tile (1, 2 or 4)
+    int bw, bh;             // tile = bw columns x bh rows, bw * bh = 128
     int tiles_x, tiles_y, n_tiles, co_pad;
     long long total_tiles;
     int wl_out[PCX_MAX_PART];
@@ -52,20 +50,6 @@ struct Cfg {
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ bool elect_one()
-{
-    uint32_t pred = 0;
-    asm volatile(
-        "{\n"
-        ".reg .b32 rx;\n"
-        ".reg .pred px;\n"
-        "elect.sync rx|px, 0xffffffff;\n"
-        "@px mov.s32 %0, 1;\n"
-        "}\n"
-        : "+r"(pred));
-    return pred != 0;
-}
-
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3)
 {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -154,10 +138,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
 }
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) [4,6), a/b format TF32 (2) [7,10) [10,13),
-// a_major MN (1) [15], b_major K (0) [16], N>>3 [17,23), M>>4 [24,29)
+// a_major K (0) [15], b_major K (0) [16], N>>3 [17,23), M>>4 [24,29)
 __host__ __device__ constexpr uint32_t instr_desc(int n)
 {
-    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+    return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
 struct Tile {
@@ -169,8 +153,8 @@ __device__ __forceinline__ Tile decode_tile(const TcParams &p, long long t)
 {
     Tile r;
     r.n0 = (int)(t % p.n_tiles); t /= p.n_tiles;
-    r.x0 = (int)(t % p.tiles_x) * (CHUNK * p.cx); t /= p.tiles_x;
-    r.y0 = (int)(t % p.tiles_y) * (4 / p.cx); t /= p.tiles_y;
+    r.x0 = (int)(t % p.tiles_x) * p.bw; t /= p.tiles_x;
+    r.y0 = (int)(t % p.tiles_y) * p.bh; t /= p.tiles_y;
     r.plane = t;
     return r;
 }
@@ -240,12 +224,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     unsigned char *sa = stage_base + (size_t)stage * C::STAGE_BYTES;
                     unsigned char *sb = sa + A_STAGE_BYTES;
                     mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const int oy = tl.y0 + c / p.cx, ox = tl.x0 + (c % p.cx) * CHUNK;
-                        tma_load_4d(sa + c * A_CHUNK_BYTES, &map_x, &full_bar[stage], ox * p.stride + kx, oy * p.stride + ky,
-                                    kb * BLOCK_K, (int)tl.plane);
-                    }
+                    tma_load_4d(sa, &map_x, &full_bar[stage], kb * BLOCK_K, tl.x0 * p.stride + kx, tl.y0 * p.stride + ky, (int)tl.plane);
                     tma_load_3d(sb, &map_w, &full_bar[stage], kb * BLOCK_K, tl.n0 * NT, tap);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -272,9 +251,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
                     for (int kk = 0; kk < BLOCK_K / UMMA_K; kk++) {
-                        // A (MN-major): K atom kk starts 1024 B further; chunks (M) are A_CHUNK_BYTES apart
-                        const uint64_t ad = smem_desc(sa + kk * 1024, A_CHUNK_BYTES, 1024);
-                        // B (K-major): 8 tf32 = 32 B further inside the 128 B row; 8-row groups 1024 B apart
+                        // both operands K-major SWIZZLE_128B: 8 tf32 = 32 B further inside the 128 B row per MMA,
+                        // 8-row groups (one swizzle atom) 1024 B apart
+                        const uint64_t ad = smem_desc(sa + kk * UMMA_K * 4, 16, 1024);
                         const uint64_t bd = smem_desc(sb + kk * UMMA_K * 4, 16, 1024);
                         umma_tf32(tmem_d, ad, bd, idesc, (it | kk) != 0);
                     }
@@ -288,15 +267,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
     } else {
         // ===================================================================================== epilogue warps
-        const int q = warp & 3;                 // TMEM lane quadrant this warp may read = chunk index
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+        const int m = q * 32 + lane;            // pixel of the tile owned by this thread
         int acc = 0;
         uint32_t acc_phase = 0;
         for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             Tile tl = decode_tile(p, t);
             const int g = (int)(tl.plane % p.npart);
             const int wl = p.wl_out[g];
-            const int oy = tl.y0 + q / p.cx;
-            const int ox = tl.x0 + (q % p.cx) * CHUNK + lane;
+            const int oy = tl.y0 + m / p.bw;
+            const int ox = tl.x0 + m % p.bw;
             const bool in_plane = oy < p.Ho && ox < p.Wo;
             const bool valid = in_plane && ox < wl;
             const bool live = tile_live(p, tl);
@@ -304,11 +284,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 mbar_wait(&acc_full[acc], acc_phase);
                 tc_fence_after();
             }
-            const int nco = min(NT, p.Co - tl.n0 * NT);
-            float *yp = y + ((tl.plane * p.Co + (long long)tl.n0 * NT) * p.out_rows + oy + p.out_y0) * (long long)p.out_pitch + ox + p.out_x0;
-            const long long ystride = (long long)p.out_rows * p.out_pitch;
-            const long long aoff = ((tl.plane * p.Co + (long long)tl.n0 * NT) * p.aux_rows + oy + p.aux_y0) * (long long)p.aux_pitch + ox + p.aux_x0;
-            const long long astride = (long long)p.aux_rows * p.aux_pitch;
+            const int nco = min(NT, p.Co - tl.n0 * NT);       // multiple of 4
+            const int cbase = tl.n0 * NT;
+            float *yp = y + (((tl.plane * p.out_rows + oy + p.out_y0) * (long long)p.out_pitch) + ox + p.out_x0) * p.Co + cbase;
+            const long long aoff = (((tl.plane * p.aux_rows + oy + p.aux_y0) * (long long)p.aux_pitch) + ox + p.aux_x0) * p.Co + cbase;
             constexpr int STEP = NT >= 32 ? 32 : 16;
 #pragma unroll 1
             for (int c0 = 0; c0 < NT; c0 += STEP) {
@@ -321,20 +300,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 }
                 if (in_plane) {
 #pragma unroll
-                    for (int j = 0; j < STEP; j++) {
+                    for (int j = 0; j < STEP; j += 4) {
                         const int co = c0 + j;
                         if (co >= nco) break;
-                        float r = 0.f;
+                        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (valid) {
-                            const int cg = tl.n0 * NT + co;
-                            r = __uint_as_float(v[j]);
-                            if (bias) r = __fadd_rn(r, __ldg(bias + cg));
-                            if (p.act == 1) { if (r < 0.f) r = __fmul_rn(r, __ldg(slope + cg)); }
-                            else if (p.act == 2) r = 1.0f / (1.0f + expf(-r));
-                            if (mul) r = __fmul_rn(r, __ldg(mul + aoff + co * astride));
-                            if (residual) r = __fadd_rn(__ldg(residual + aoff + co * astride), r);
+                            r = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                            if (bias) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + cbase + co));
+                                r.x = __fadd_rn(r.x, b4.x); r.y = __fadd_rn(r.y, b4.y); r.z = __fadd_rn(r.z, b4.z); r.w = __fadd_rn(r.w, b4.w);
+                            }
+                            if (p.act == 1) {
+                                const float4 s4 = __ldg(reinterpret_cast<const float4 *>(slope + cbase + co));
+                                if (r.x < 0.f) r.x = __fmul_rn(r.x, s4.x);
+                                if (r.y < 0.f) r.y = __fmul_rn(r.y, s4.y);
+                                if (r.z < 0.f) r.z = __fmul_rn(r.z, s4.z);
+                                if (r.w < 0.f) r.w = __fmul_rn(r.w, s4.w);
+                            } else if (p.act == 2) {
+                                r.x = 1.0f / (1.0f + expf(-r.x)); r.y = 1.0f / (1.0f + expf(-r.y));
+                                r.z = 1.0f / (1.0f + expf(-r.z)); r.w = 1.0f / (1.0f + expf(-r.w));
+                            }
+                            if (mul) {
+                                const float4 m4 = __ldg(reinterpret_cast<const float4 *>(mul + aoff + co));
+                                r.x = __fmul_rn(r.x, m4.x); r.y = __fmul_rn(r.y, m4.y); r.z = __fmul_rn(r.z, m4.z); r.w = __fmul_rn(r.w, m4.w);
+                            }
+                            if (residual) {
+                                const float4 a4 = __ldg(reinterpret_cast<const float4 *>(residual + aoff + co));
+                                r.x = __fadd_rn(a4.x, r.x); r.y = __fadd_rn(a4.y, r.y); r.z = __fadd_rn(a4.z, r.z); r.w = __fadd_rn(a4.w, r.w);
+                            }
                         }
-                        yp[co * ystride] = r;
+                        *reinterpret_cast<float4 *>(yp + co) = r;
                     }
                 }
             }
@@ -447,7 +442,10 @@ int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w,
     cudaStream_t s = (cudaStream_t)stream;
     const int nt = n_tile_for(d.Co);
     PCX_REQUIRE(nt != 0 && d.Ci % BLOCK_K == 0, "tensor-core conv needs Co <= 16 or a multiple of 96 and Ci a multiple of 32 (Co=%d Ci=%d); use impl=1", d.Co, d.Ci);
-    PCX_REQUIRE(d.in_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15) == 0, "TMA needs a 16-byte aligned input with a pitch that is a multiple of 4 floats (pitch=%d); use impl=1", d.in_pitch);
+    PCX_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_y) & 15) == 0, "tensor-core conv needs 16-byte aligned NHWC buffers");
+    PCX_REQUIRE(d.Co % 4 == 0, "tensor-core conv needs Co %% 4 == 0 (got %d)", d.Co);
+    const int bw = d.Wo >= 512 ? 128 : (d.Wo >= 256 ? 64 : 32);
+    const int bh = BLOCK_M / bw;
     EncodeTiledFn enc = encode_tiled();
     PCX_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
 
@@ -476,10 +474,10 @@ int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w,
     CUtensorMap mx, mw;
     {
         const long long planes = (long long)d.N * d.npart;
-        cuuint64_t dims[4] = {(cuuint64_t)d.in_pitch, (cuuint64_t)d.Hi, (cuuint64_t)d.Ci, (cuuint64_t)planes};
-        cuuint64_t strides[3] = {(cuuint64_t)d.in_pitch * 4, (cuuint64_t)d.in_pitch * d.Hi * 4, (cuuint64_t)d.in_pitch * d.Hi * d.Ci * 4};
-        cuuint32_t box[4] = {(cuuint32_t)(CHUNK * d.stride), 1, BLOCK_K, 1};
-        cuuint32_t estr[4] = {(cuuint32_t)d.stride, 1, 1, 1};
+        cuuint64_t dims[4] = {(cuuint64_t)d.Ci, (cuuint64_t)d.in_pitch, (cuuint64_t)d.Hi, (cuuint64_t)planes};
+        cuuint64_t strides[3] = {(cuuint64_t)d.Ci * 4, (cuuint64_t)d.Ci * d.in_pitch * 4, (cuuint64_t)d.Ci * d.in_pitch * d.Hi * 4};
+        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)(bw * d.stride), (cuuint32_t)(bh * d.stride), 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
         CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(d_x), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -501,9 +499,9 @@ int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w,
     p.out_rows = d.out_rows; p.out_pitch = d.out_pitch; p.out_y0 = d.out_y0; p.out_x0 = d.out_x0;
     p.aux_rows = d.aux_rows; p.aux_pitch = d.aux_pitch; p.aux_y0 = d.aux_y0; p.aux_x0 = d.aux_x0;
     p.k = d.k; p.stride = d.stride; p.act = d.act;
-    p.cx = d.Wo >= 128 ? 4 : (d.Wo >= 64 ? 2 : 1);
-    p.tiles_x = (d.Wo + CHUNK * p.cx - 1) / (CHUNK * p.cx);
-    p.tiles_y = (d.Ho + (4 / p.cx) - 1) / (4 / p.cx);
+    p.bw = bw; p.bh = bh;
+    p.tiles_x = (d.Wo + bw - 1) / bw;
+    p.tiles_y = (d.Ho + bh - 1) / bh;
     p.n_tiles = co_pad / nt;
     p.co_pad = co_pad;
     p.total_tiles = (long long)p.planes * p.tiles_y * p.tiles_x * p.n_tiles;

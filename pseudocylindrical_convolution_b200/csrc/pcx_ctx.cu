@@ -179,7 +179,7 @@ __global__ void dextract_kernel(const float *__restrict__ in, float *__restrict_
 // Expression shapes follow the reference's SASS: float v, FMUL s2*(v-mu), IEEE float division, erff,
 // DFMA(erf, .5, .5), DFMA(f, w, ps) rounded to float per component, FMUL total*ps, DADD .5, truncation.
 __global__ void gmm_table_kernel(float *__restrict__ logit, float *__restrict__ delta, const float *__restrict__ mean, int n,
-                                 int ng, int nstep, float bias, float total, float beta, float *__restrict__ cdf_f,
+                                 int ng, int nstep, float bias, float total, float beta, int form, float *__restrict__ cdf_f,
                                  int *__restrict__ cdf_i)
 {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -210,8 +210,18 @@ __global__ void gmm_table_kernel(float *__restrict__ logit, float *__restrict__ 
     for (int pt = 1; pt < nstep; pt++) {
         float v = pt - 1 - bias + 0.5;
         float ps = 0;
-        for (int i = 0; i < ng; i++) {
-            ps = ps + w[i] * (0.5 + 0.5 * erf(s2 * (v - mu[i]) / d[i]));
+        if (form == 0) {
+            // entropy_gmm_table_batch_forward_kernel (:146-150): the whole term stays in double, one rounding per component
+            for (int i = 0; i < ng; i++) {
+                ps = ps + w[i] * (0.5 + 0.5 * erf(s2 * (v - mu[i]) / d[i]));
+            }
+        } else {
+            // entropy_gmm_table_forward_kernel (:69-72): f is stored to float first, then a float FFMA
+            float f;
+            for (int i = 0; i < ng; i++) {
+                f = 0.5 + 0.5 * erf(s2 * (v - mu[i]) / d[i]);
+                ps = ps + w[i] * f;
+            }
         }
         c[pt] = (float)static_cast<int>(total * ps + 0.5);
     }
@@ -372,14 +382,15 @@ int pcx_dextract_step(const float *d_in, float *d_out, int nrep, int npart, int 
 }
 
 int pcx_gmm_table(float *d_logit, float *d_delta, const float *d_mean, int n, int ng, int nstep, float bias, float total,
-                  float beta, float *d_cdf_f, int *d_cdf_i, void *stream)
+                  float beta, int form, float *d_cdf_f, int *d_cdf_i, void *stream)
 {
     PCX_REQUIRE(d_logit && d_delta && d_mean && (d_cdf_f || d_cdf_i), "null pointer");
     PCX_REQUIRE(ng >= 1 && ng <= PCX_MAX_GAUSS, "num_gaussian %d > 16 (entropy_gmm_table_cuda.cu:13)", ng);
     PCX_REQUIRE(nstep >= 2 && nstep <= 32, "nstep %d out of range", nstep);
+    PCX_REQUIRE(form == 0 || form == 1, "form %d", form);
     if (n <= 0) return PCX_OK;                                             // tn > 0 (:163)
     gmm_table_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(d_logit, d_delta, d_mean, n, ng, nstep, bias, total,
-                                                                         beta, d_cdf_f, d_cdf_i);
+                                                                         beta, form, d_cdf_f, d_cdf_i);
     PCX_LAUNCHED();
     return PCX_OK;
 }

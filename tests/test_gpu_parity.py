@@ -428,50 +428,58 @@ def test_errors_are_loud(P, cuda):
 @pytest.mark.parametrize("Ci,Co,k,s,act,h,W", [
     (96, 96, 3, 1, 1, 8, 128),      # ResidualBlock conv2
     (192, 192, 3, 1, 1, 8, 128),    # ResidualBlockV2
-    (192, 96, 1, 1, 1, 10, 132),    # ResidualBlock conv1 on the padded tile
+    (192, 96, 1, 1, 1, 10, 130),    # ResidualBlock conv1 on the padded tile (odd pitch)
     (96, 192, 1, 1, 0, 8, 128),     # ResidualBlock conv3 (+ residual)
-    (192, 768, 3, 1, 1, 4, 64),     # ResidualBlockUp conv1 (4 N-tiles, 2 chunks per row)
+    (192, 768, 3, 1, 1, 4, 64),     # ResidualBlockUp conv1 (4 N-tiles)
     (192, 12, 3, 1, 0, 8, 128),     # last decoder layer (N padded to 16)
     (192, 192, 3, 2, 1, 8, 128),    # ResidualBlockDown conv1 (TMA element stride 2)
     (192, 192, 1, 2, 0, 8, 128),    # ResidualBlockDown shortcut
-    (192, 192, 1, 1, 2, 2, 64),     # code layer: sigmoid, tiny tiles (1 chunk per row)
+    (192, 192, 1, 1, 2, 2, 64),     # code layer: sigmoid, tiny planes
+    (32, 192, 3, 2, 1, 16, 256),    # first layer: 3 input channels zero-padded to 32
+    (192, 192, 3, 1, 1, 4, 512),    # wide rows: 128x1 tiles
+    (96, 96, 3, 1, 1, 6, 320),      # 64x2 tiles, ragged rows
 ])
 def test_conv_tensor_core_vs_direct(cuda, orc, Ci, Co, k, s, act, h, W):
-    """tcgen05 TF32 implicit GEMM against the fp32 CUDA-core direct form on the same device.  Tolerance: TF32
-    operands carry 10 explicit mantissa bits (activations truncated by the MMA, weights rounded when packed), so
-    |err| <= ~2^-10 * sum|x||w|; checked as 4e-3 * sqrt(K) * rms(x) * rms(w) absolute, far below one quantiser step."""
+    """tcgen05 TF32 implicit GEMM (NHWC) against the fp32 CUDA-core direct form (NCHW) on the same device.
+    Tolerance: TF32 operands carry 10 explicit mantissa bits (activations truncated by the MMA, weights rounded
+    when packed): per-output error ~ 2^-11 * sqrt(K) * rms(x) * rms(w) ~ 5e-4 here; asserted rms < 1.5e-3 and
+    max < 1e-2 (x the gate magnitude), far below one quantiser step (~0.11)."""
     import ctypes as C
     import torch
     from pseudocylindrical_convolution_b200._lib import call
     rng = np.random.default_rng(31)
     halo = 2 if k == 3 else 0
     Hi, Wi = h + halo, W + halo
-    pitch = (Wi + 3) // 4 * 4
     ho, wo = (Hi - k) // s + 1, (Wi - k) // s + 1
-    wl = [min(int(v), wo) for v in orc.band_widths(W64, 16 * 4, wo // 2 * 2 if wo % 64 else wo)] if wo % 64 == 0 else [wo - (g % 5) for g in range(16)]
-    x = np.zeros((16, Ci, Hi, pitch), np.float32)
-    x[..., :Wi] = rng.standard_normal((16, Ci, Hi, Wi)).astype(np.float32)
+    wl = [max(4, wo - 7 * (g % 5)) for g in range(16)]
+    wl[3] = min(wo, 20)                                           # a band whose right-hand tiles are all invalid
+    x = rng.standard_normal((16, Ci, Hi, Wi)).astype(np.float32)
     w = (rng.standard_normal((Co, Ci, k, k)) / np.sqrt(Ci * k * k)).astype(np.float32)
     b = rng.standard_normal(Co).astype(np.float32)
     slope = rng.random(Co).astype(np.float32) * 0.5
-    opitch = (wo + 3) // 4 * 4
-    res = rng.standard_normal((16, Co, ho, opitch)).astype(np.float32)
-    mul = rng.standard_normal((16, Co, ho, opitch)).astype(np.float32)
-    outs = []
-    for impl in (1, 0):
-        d, Ho, Wo = _conv_desc(16, Ci, Hi, Wi, Co, k, s, act, wl, impl)
-        d.in_pitch = pitch
-        d.out_pitch = d.aux_pitch = opitch
-        y = torch.full((16, Co, Ho, opitch), -7.0, device=cuda)
-        dx, dw, db, ds, dm, dr = (T(a, cuda) for a in (x, w, b, slope, mul, res))
-        call("pcx_conv2d_fwd", C.byref(d), *(C.c_void_p(t.data_ptr()) for t in (dx, dw, db, ds, dm, dr, y)), None)
-        torch.cuda.synchronize()
-        outs.append(N(y))
-    direct, tc = outs
-    assert (tc[..., wo:] == -7.0).all(), "pitch slack must stay untouched"
+    res = rng.standard_normal((16, Co, ho, wo)).astype(np.float32)
+    mul = rng.standard_normal((16, Co, ho, wo)).astype(np.float32)
+    dx, dw, db, ds, dm, dr = (T(a, cuda) for a in (x, w, b, slope, mul, res))
+    # direct, NCHW
+    d, Ho, Wo = _conv_desc(16, Ci, Hi, Wi, Co, k, s, act, wl, 1)
+    y1 = torch.empty((16, Co, Ho, Wo), device=cuda)
+    call("pcx_conv2d_fwd", C.byref(d), *(C.c_void_p(t.data_ptr()) for t in (dx, dw, db, ds, dm, dr, y1)), None)
+    # tensor core, NHWC, output written into the interior of a larger (padded) plane
+    d, Ho, Wo = _conv_desc(16, Ci, Hi, Wi, Co, k, s, act, wl, 0)
+    d.out_rows, d.out_pitch, d.out_y0, d.out_x0 = Ho + 2, Wo + 3, 1, 2
+    xh, mh, rh = (t.permute(0, 2, 3, 1).contiguous() for t in (dx, dm, dr))
+    y0 = torch.full((16, Ho + 2, Wo + 3, Co), -7.0, device=cuda)
+    call("pcx_conv2d_fwd", C.byref(d), *(C.c_void_p(t.data_ptr()) for t in (xh, dw, db, ds, mh, rh, y0)), None)
+    torch.cuda.synchronize()
+    direct = N(y1)
+    full = N(y0)
+    tc = full[:, 1:1 + Ho, 2:2 + Wo, :].transpose(0, 3, 1, 2)
+    border = full.copy()
+    border[:, 1:1 + Ho, 2:2 + Wo, :] = -7.0
+    assert (border == -7.0).all(), "cells outside the output window must stay untouched"
     for g in range(16):
-        assert (tc[g, :, :, wl[g]:wo] == 0).all()
-    tol = 4e-3 * np.sqrt(Ci * k * k) * 1.0 * (1.0 / np.sqrt(Ci * k * k)) * (np.abs(mul).max() if act != 2 else 1.0)
-    err = np.abs(tc[..., :wo] - direct[..., :wo])
-    assert err.max() < max(tol, 4e-3) * 4, "max err %g" % err.max()
-    assert np.sqrt((err ** 2).mean()) < 2e-3
+        assert (tc[g, :, :, wl[g]:] == 0).all()
+    err = np.abs(tc - direct)
+    scale = max(1.0, float(np.abs(mul).max())) if act != 2 else float(np.abs(mul).max())
+    assert np.sqrt((err ** 2).mean()) < 1.5e-3, "rms err %g" % np.sqrt((err ** 2).mean())
+    assert err.max() < 1e-2 * scale, "max err %g" % err.max()
