@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200 pseudocylindrical codec hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host cores (CPU port)
+
+Workload (BASELINE.json configs[1], named in `config.workload`): the tile pipeline
+    sphere_slice -> pseudo_pad(1) -> pseudocylindrical conv 3x3 (192 -> 192 channels) -> pseudo_fill -> sphere_uslice
+on a batch of 16 synthetic ERP tensors of 192 x 1024 x 2048 float32 PER GPU (images are sharded across GPUs with
+no collective on the data path: weak scaling).  One "step" = one pass over the batch.  Metric: ERP megapixels/s =
+images * H * W / 1e6 / seconds, whole job.
+
+  value  : inputs and outputs resident in HBM (25.8 GB in, 25.8 GB out per GPU - far larger than the 126 MB L2, so
+           every step streams from DRAM and no L2 flush is needed), timed with CUDA events, max over ranks.
+  e2e    : the same call on pinned HOST buffers (TilePipeline.forward_host): H2D of every image, kernels, D2H of
+           every result inside the timed region, copies overlapped with compute on separate streams.
+  roofline: the dominant kernel (tcgen05 implicit-GEMM convolution) timed live with CUDA events around its
+           launches; algorithmic FLOPs = 2*9*Ci*Co*sum_g(h*wl[g]) per image.  TF32 tensor peak is
+           taken as HALF the measured bf16 peak of MEASURED_PEAKS.json (kind::tf32 issues at half the f16 rate).
+           `roofline_hbm` adds the two HBM-bound gathers against the measured copy bandwidth.
+  cpu_baseline: the CPU port (oracle/ C restatement for slice/pad/fill/uslice + torch-CPU fp32 conv2d) on ONE
+           image of the same workload, all host threads, rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CI, CO, H, W, BATCH, NPART = 192, 192, 1024, 2048, 16, 16
+METRIC = "erp_megapixels_per_s_tile_pipeline"
+UNIT = "MP/s"
+WORKLOAD = "configs[1] tile pipeline: slice->pad(1)->pconv3x3(192->192)->fill->uslice, batch 16 x 192x1024x2048 fp32 per GPU"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16": float(p["bf16_tflops"]),
+                "bf16_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+
+
+def band_widths(Wd):
+    w64 = [15, 31, 54, 63, 63, 64, 64, 64, 64, 64, 64, 63, 63, 54, 31, 15]
+    import numpy as np
+    return [int(float(np.float32(np.float32(w) / np.float32(64) * np.float32(Wd))) + 0.5) for w in w64]
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples of one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], 0, set(), 0.0
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1])); power = max(power, float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "power_w_max": power or None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synthetic_image(gen_seed, device):
+    """Smooth low-frequency field + noise in [0,1], generated on the device to keep set-up short."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(1234 + gen_seed)
+    low = torch.rand((1, CI, H // 32, W // 32), generator=g, device=device)
+    up = torch.nn.functional.interpolate(low, size=(H, W), mode="bilinear", align_corners=False)[0]
+    return (0.8 * up + 0.2 * torch.rand((CI, H, W), generator=g, device=device)).contiguous()
+
+
+def make_pipeline(device_index):
+    import torch
+    from pseudocylindrical_convolution_b200.tile_pipeline import TilePipeline
+    torch.manual_seed(0)
+    pipe = TilePipeline(CI, CO, npart=NPART, opt=True, act=True, device=device_index)
+    return pipe
+
+
+# ------------------------------------------------------------------------------------------------ CPU port
+def cpu_port_step(x_np, weight, bias, slope, threads):
+    """One image through the CPU restatement of the reference operators (oracle/) + torch-CPU conv2d."""
+    import numpy as np
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as orc
+    wl = orc.band_widths(orc.W64_NPART16, H, W)
+    C = x_np.shape[1]
+    chunks = [(c, min(c + max(1, C // threads), C)) for c in range(0, C, max(1, C // threads))]
+
+    def front(cs):
+        t = orc.sphere_slice(x_np[:, cs[0]:cs[1]], wl)
+        return orc.pseudo_pad(t, wl, 1)
+
+    with ThreadPoolExecutor(threads) as ex:
+        padded = np.concatenate(list(ex.map(front, chunks)), axis=1)
+    torch.set_num_threads(threads)
+    with torch.no_grad():
+        y = torch.nn.functional.conv2d(torch.from_numpy(padded), weight, bias)
+        y = torch.where(y < 0, y * slope.view(1, -1, 1, 1), y).numpy()
+
+    def back(cs):
+        return orc.sphere_uslice(orc.pseudo_fill(y[:, cs[0]:cs[1]], wl), wl)
+
+    Co = y.shape[1]
+    ochunks = [(c, min(c + max(1, Co // threads), Co)) for c in range(0, Co, max(1, Co // threads))]
+    with ThreadPoolExecutor(threads) as ex:
+        return np.concatenate(list(ex.map(back, ochunks)), axis=1)
+
+
+def time_cpu_port(steps, warmup):
+    import numpy as np
+    import torch
+    from oracle import oracle as orc
+    orc.build()
+    threads = os.cpu_count() or 1
+    rng = np.random.default_rng(1234)
+    x = rng.random((1, CI, H, W), dtype=np.float32)
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(CI, CO, 3, 1)
+    slope = torch.full((CO,), 0.25)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        cpu_port_step(x, conv.weight.detach(), conv.bias.detach(), slope, threads)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    mean = sum(times) / len(times)
+    return (H * W / 1e6) / mean, mean, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    value, sec, threads = time_cpu_port(steps, warm)
+    sample = "1 image 192x1024x2048 per step (of the 16-image batch), %d timed steps" % steps
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from pseudocylindrical_convolution_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.call("pcx_device_check", local, None, None)
+    lib = _lib.load()
+    peaks = load_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    pipe = make_pipeline(local)
+    nimg = args.batch
+    x = torch.empty((nimg, CI, H, W), dtype=torch.float32, device=dev)
+    for i in range(nimg):
+        x[i] = synthetic_image(rank * nimg + i, dev)
+    out = torch.empty((nimg, CO, H, W), dtype=torch.float32, device=dev)
+
+    # ---- device-resident throughput, with per-kernel event timing of the three launches of every image
+    class Prof:
+        def __init__(self):
+            self.ev = {"slice_pad": [], "conv": [], "uslice": []}
+    prof = Prof()
+    orig_call = _lib.call
+    timed = {"on": False}
+    names = {"pcx_slice_pad_nhwc": "slice_pad", "pcx_conv2d_fwd": "conv", "pcx_uslice_nhwc": "uslice"}
+
+    def call_hook(name, *a):
+        if timed["on"] and name in names:
+            s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = orig_call(name, *a)
+            e.record()
+            prof.ev[names[name]].append((s, e))
+            return r
+        return orig_call(name, *a)
+
+    import pseudocylindrical_convolution_b200.tile_pipeline as tp
+    tp.call = call_hook
+
+    for _ in range(args.warmup):
+        pipe(x, out)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = lib.pcx_launch_count()
+    timed["on"] = True
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for _ in range(args.steps):
+        pipe(x, out)
+    t1.record()
+    barrier()
+    timed["on"] = False
+    launches = lib.pcx_launch_count() - launches0
+    clocks = sampler.stop()
+    ms = t0.elapsed_time(t1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    mp_step = world * nimg * H * W / 1e6
+    value = mp_step / (ms / 1e3)
+
+    def avg_ms(key):
+        ev = prof.ev[key]
+        return sum(s.elapsed_time(e) for s, e in ev) / max(1, len(ev))
+    k_ms = {k: avg_ms(k) for k in prof.ev}
+    wl = band_widths(W)
+    h = H // NPART
+    valid = sum(h * w for w in wl)
+    flops_conv = 2.0 * 9 * CI * CO * valid                       # per launch (one image)
+    tf32_peak = peaks["bf16_sustained"] / 2.0
+    conv_tflops = flops_conv / (k_ms["conv"] / 1e3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("conv_dram_bytes_per_launch")
+    roofline = {"kernel": "conv_tc_kernel<192> (tcgen05 kind::tf32, 128x192 tiles)", "bound": "tensor", "achieved": conv_tflops,
+                "peak": tf32_peak, "unit": "TFLOP/s", "frac": conv_tflops / tf32_peak, "traffic": traffic,
+                "peak_source": "%s bf16_tflops_sustained / 2 (tf32 issues at half the f16 rate)" % peaks["source"],
+                "flops_per_launch": flops_conv, "avg_launch_ms": k_ms["conv"], "share_of_step": k_ms["conv"] * nimg / ms}
+    bytes_sp = 4.0 * (CI * H * W + CI * sum((h + 2) * (w + 2) for w in wl))          # read ERP + write valid padded tiles
+    bytes_us = 4.0 * (CO * valid + CO * H * W)                                          # read valid tiles + write ERP
+    roofline_hbm = [
+        {"kernel": "slice_pad_nhwc_kernel", "bound": "hbm", "achieved": bytes_sp / (k_ms["slice_pad"] / 1e3) / 1e9, "peak": peaks["hbm_gbs"],
+         "unit": "GB/s", "frac": bytes_sp / (k_ms["slice_pad"] / 1e3) / 1e9 / peaks["hbm_gbs"], "avg_launch_ms": k_ms["slice_pad"],
+         "bytes_per_launch": bytes_sp, "share_of_step": k_ms["slice_pad"] * nimg / ms},
+        {"kernel": "uslice_nhwc_kernel", "bound": "hbm", "achieved": bytes_us / (k_ms["uslice"] / 1e3) / 1e9, "peak": peaks["hbm_gbs"],
+         "unit": "GB/s", "frac": bytes_us / (k_ms["uslice"] / 1e3) / 1e9 / peaks["hbm_gbs"], "avg_launch_ms": k_ms["uslice"],
+         "bytes_per_launch": bytes_us, "share_of_step": k_ms["uslice"] * nimg / ms},
+    ]
+
+    # ---- end to end through the public call on pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        slots = min(4, nimg)
+        xh = [torch.empty((CI, H, W), dtype=torch.float32).pin_memory() for _ in range(slots)]
+        oh = [torch.empty((CO, H, W), dtype=torch.float32).pin_memory() for _ in range(slots)]
+        for i in range(slots):
+            xh[i].copy_(x[i])
+        xs = [xh[i % slots] for i in range(nimg)]
+        os_ = [oh[i % slots] for i in range(nimg)]
+        pipe.forward_host(xs[:2], os_[:2])
+        barrier()
+        e_steps = max(1, min(args.steps, 3))
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        t0.record()
+        for _ in range(e_steps):
+            pipe.forward_host(xs, os_)
+            checksum = float(oh[0][0, 0, :8].sum())          # host read of a result
+        t1.record()
+        barrier()
+        e_ms = max(t0.elapsed_time(t1), (time.perf_counter() - w0) * 1e3) / e_steps
+        if world > 1:
+            t = torch.tensor([e_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+        e2e = {"value": mp_step / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 4 * CI * H * W * nimg,
+               "d2h_bytes_per_step": 4 * CO * H * W * nimg, "ms_per_step": e_ms, "steps": e_steps, "checksum": checksum}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, sec, threads = time_cpu_port(1, 0)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "1 image 192x1024x2048 (1/16 of a step), 1 run, %.1f s" % sec}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate)",
+                "data": "synthetic", "config": {"workload": WORKLOAD, "images_per_gpu": nimg, "l2": "inputs (25.8 GB/GPU) exceed L2, no flush",
+                                                "parallelism": "image-sharded x%d, no collective" % world},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_hbm": roofline_hbm,
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="pcx", choices=["pcx", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU per step (default: the config's 16)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -95,6 +95,18 @@ int pcx_entropy_pad_fwd(const float *d_in, float *d_out, int N, int C, int h, in
 int pcx_halo_fill(float *d_buf, int N, int C, int h, int W, int npart, int pad, const int *wl,
                   const int *d_band, const int *d_row, const int *d_col, const float *d_tw,
                   int pitch, void *stream);
+/* B200-native fused forms used by the tensor-core transforms (channels-last tiles):
+ * SphereSliceOp.forward + PseudoPadOp.forward in one pass (sphere_slice_cuda.cu:87-116, pseudo_pad.cu:39-96):
+ * in (N,C,H,W) NCHW -> out [N*npart][H/npart + 2*pad][out_pitch][C]; d_src/d_wt from pcx_slice_table, halo tables
+ * from pcx_halo_table(mode 0) (ignored when pad == 0).  Values are bit-identical to slice followed by pad.
+ * zero_invalid != 0 also writes the zeros of the columns >= wl + 2*pad (skip it for pre-zeroed buffers). */
+int pcx_slice_pad_nhwc(const float *d_in, float *d_out, int N, int C, int H, int W, int npart, int pad, const int *wl,
+                       const int *d_src, const float *d_wt, const int *d_band, const int *d_row, const int *d_col,
+                       const float *d_tw, int out_pitch, int zero_invalid, void *stream);
+/* SphereUsliceOp.forward (sphere_uslice_cuda.cu:73-99) reading channels-last tiles
+ * [N*npart][in_rows][in_pitch][C] whose band data start at (in_y0, in_x0); out (N,C,h*npart,W) NCHW. */
+int pcx_uslice_nhwc(const float *d_in, float *d_out, int N, int C, int h, int W, int npart, int in_rows, int in_pitch,
+                    int in_y0, int in_x0, const int *wl, const int *d_src, const float *d_wt, void *stream);
 /* PseudoFillOp.forward    (main.cpp:103-107 -> pseudo_fill_cuda.cu:46-61), in place. */
 int pcx_fill(float *d_data, int N, int C, int Hh, int Ww, int npart, int pad, int trim, const int *wl,
              float fvalue, void *stream);
@@ -123,7 +135,8 @@ int pcx_dquant_fwd(const float *d_sym, const float *d_theta, float *d_centres, f
  * impl: 0 = tcgen05/TMEM implicit GEMM (TF32 operands, fp32 accumulate); tensors are NHWC
  *           (x [plane][Hi][in_pitch][Ci], y [plane][out_rows][out_pitch][Co], aux likewise), Ci % 32 == 0,
  *           Co <= 16 or Co % 96 == 0;
- *       1 = fp32 CUDA-core direct form on NCHW tensors (exact-order reference used to validate impl 0). */
+ *       1 = fp32 CUDA-core direct form on NCHW tensors (exact-order reference used to validate impl 0);
+ *       2 = as 0, but d_w is already packed by pcx_conv_pack_weights (no per-call repack). */
 typedef struct pcx_conv_desc {
     int N, npart;            /* images, bands per image */
     int Ci, Hi, in_pitch;    /* input planes: Hi rows of in_pitch floats */
@@ -132,7 +145,7 @@ typedef struct pcx_conv_desc {
     int out_y0, out_x0;      /* where (0,0) of the result lands inside the output plane */
     int k, stride;           /* 1 or 3; 1 or 2 */
     int act;                 /* 0 none, 1 PReLU, 2 sigmoid */
-    int impl;                /* 0 tensor core, 1 fp32 direct */
+    int impl;                /* 0 tensor core, 1 fp32 direct, 2 tensor core with pre-packed weights */
     int aux_rows, aux_pitch; /* geometry shared by the optional d_mul / d_residual planes (Co channels) */
     int aux_y0, aux_x0;
     int wl_out[PCX_MAX_PART];/* valid output width per band (columns >= wl_out are written as 0) */

@@ -45,6 +45,8 @@ PROTOTYPES = {
     "pcx_pad_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _IP, _P, _P, _P, _P, _I, _P]),
     "pcx_entropy_pad_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _IP, _P, _P, _P, _P, _P]),
     "pcx_halo_fill": (_I, [_P, _I, _I, _I, _I, _I, _I, _IP, _P, _P, _P, _P, _I, _P]),
+    "pcx_slice_pad_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _IP, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "pcx_uslice_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _IP, _P, _P, _P]),
     "pcx_fill": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _IP, _F, _P]),
     "pcx_dtow": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "pcx_quant_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _IP, _P]),

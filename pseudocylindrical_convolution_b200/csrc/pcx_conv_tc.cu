@@ -449,26 +449,32 @@ int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w,
     EncodeTiledFn enc = encode_tiled();
     PCX_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
 
-    // ---- weights: repack once per (pointer, shape); d_w is the caller's OIHW tensor
+    // ---- weights: impl 2 = d_w is already in the packed [tap][Co_pad][Ci] layout (pcx_conv_pack_weights);
+    //      impl 0 = d_w is the caller's OIHW tensor, repacked into a cached scratch buffer on every call (the
+    //      tensor may have been updated in place; the repack is <= 5 MB)
     const int co_pad = (d.Co + nt - 1) / nt * nt;
     float *packed = nullptr;
-    {
-        std::lock_guard<std::mutex> lock(g_pack_mutex);
-        for (auto &e : g_pack_cache)
-            if (e.src == d_w && e.Co == d.Co && e.Ci == d.Ci && e.k == d.k) { packed = e.dst; break; }
-        if (!packed) {
-            PackedWeights &e = g_pack_cache[g_pack_next];
-            g_pack_next = (g_pack_next + 1) % 512;
-            if (e.dst) cudaFree(e.dst);
-            size_t n = (size_t)d.k * d.k * co_pad * d.Ci;
-            PCX_CUDA(cudaMalloc(&e.dst, n * sizeof(float)));
-            e.src = d_w; e.Co = d.Co; e.Ci = d.Ci; e.k = d.k; e.co_pad = co_pad;
-            packed = e.dst;
+    if (d.impl == 2) {
+        PCX_REQUIRE((reinterpret_cast<uintptr_t>(d_w) & 15) == 0, "packed weights must be 16-byte aligned");
+        packed = const_cast<float *>(d_w);
+    } else {
+        {
+            std::lock_guard<std::mutex> lock(g_pack_mutex);
+            for (auto &e : g_pack_cache)
+                if (e.src == d_w && e.Co == d.Co && e.Ci == d.Ci && e.k == d.k) { packed = e.dst; break; }
+            if (!packed) {
+                PackedWeights &e = g_pack_cache[g_pack_next];
+                g_pack_next = (g_pack_next + 1) % 512;
+                if (e.dst) cudaFree(e.dst);
+                size_t n = (size_t)d.k * d.k * co_pad * d.Ci;
+                PCX_CUDA(cudaMalloc(&e.dst, n * sizeof(float)));
+                e.src = d_w; e.Co = d.Co; e.Ci = d.Ci; e.k = d.k; e.co_pad = co_pad;
+                packed = e.dst;
+            }
         }
+        long long rc = pcx_conv_pack_weights(d_w, packed, d.Co, d.Ci, d.k, stream);
+        if (rc < 0) return (int)rc;
     }
-    // weights may have been updated in place (load_state_dict): repacking is cheap (<= 5 MB), do it every call
-    long long rc = pcx_conv_pack_weights(d_w, packed, d.Co, d.Ci, d.k, stream);
-    if (rc < 0) return (int)rc;
 
     // ---- tensor maps
     CUtensorMap mx, mw;

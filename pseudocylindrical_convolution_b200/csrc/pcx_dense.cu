@@ -215,7 +215,7 @@ int pcx_conv2d_fwd(const pcx_conv_desc *desc, const float *d_x, const float *d_w
     PCX_REQUIRE(d.act != 1 || d_slope, "PReLU needs slopes");
     if (d_mul || d_residual)
         PCX_REQUIRE(d.aux_y0 >= 0 && d.aux_x0 >= 0 && d.aux_y0 + d.Ho <= d.aux_rows && d.aux_x0 + d.Wo <= d.aux_pitch, "aux window outside the aux plane");
-    if (d.impl == 0) return pcx_conv2d_tc(desc, d_x, d_w, d_bias, d_slope, d_mul, d_residual, d_y, stream);
+    if (d.impl == 0 || d.impl == 2) return pcx_conv2d_tc(desc, d_x, d_w, d_bias, d_slope, d_mul, d_residual, d_y, stream);
     PCX_REQUIRE(d.impl == 1, "impl %d", d.impl);
     ConvGeom G;
     G.d = d;
