@@ -1,6 +1,6 @@
 """`coder` - mirror of the reference's arithmetic-coder module (coder/python.cpp:63-72) over libpcx's host
 range coder (csrc/pcx_coder.cpp).  Same class name and the same eight methods; the bitstream is
-byte-identical to the reference's (tests/test_coder.py compares against oracle/_ref/coder_ref.so)."""
+byte-identical to the reference's (tests/test_oracle_cpu.py compares against the compiled reference coder)."""
 import ctypes as C
 
 import numpy as np
