@@ -281,7 +281,7 @@ def run_gpu(args):
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("conv_dram_bytes_per_launch")
-    roofline = {"kernel": "conv_tc_kernel<192> (tcgen05 kind::tf32, 128x192 tiles)", "bound": "tensor", "achieved": conv_tflops,
+    roofline = {"kernel": "conv_pair_kernel<192> (tcgen05 cta_group::2 kind::tf32, 256x192 tiles per CTA pair, halo-tile taps)", "bound": "tensor", "achieved": conv_tflops,
                 "peak": tf32_peak, "unit": "TFLOP/s", "frac": conv_tflops / tf32_peak, "traffic": traffic,
                 "peak_source": "%s bf16_tflops_sustained / 2 (tf32 issues at half the f16 rate)" % peaks["source"],
                 "flops_per_launch": flops_conv, "avg_launch_ms": k_ms["conv"], "share_of_step": k_ms["conv"] * nimg / ms}

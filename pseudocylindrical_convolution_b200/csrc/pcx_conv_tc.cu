@@ -19,6 +19,7 @@
 #include "pcx_common.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace {
 
@@ -27,6 +28,8 @@ constexpr int BLOCK_K = 32;           // input channels per pipeline stage (= on
 constexpr int UMMA_K = 8;             // tf32
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;     // 16 KB: 128 pixel rows x 128 B
 constexpr int NUM_THREADS = 192;      // 6 warps
+constexpr int MAX_CO_STAGED = 1024;   // bias + PReLU slope vectors staged in shared memory (2 x 4 KB)
+constexpr int VEC_SMEM = 2 * MAX_CO_STAGED * 4;
 
 struct TcParams {
     int planes, npart;
@@ -37,6 +40,7 @@ struct TcParams {
     int bw, bh;             // tile = bw columns x bh rows, bw * bh = 128
     int tiles_x, tiles_y, n_tiles, co_pad;
     long long total_tiles;
+    long long *dbg;         // optional per-CTA wait-time counters of the MMA thread (PCX_TC_DEBUG), else NULL
     int wl_out[PCX_MAX_PART];
 };
 
@@ -46,7 +50,7 @@ struct Cfg {
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
     static constexpr int TMEM_COLS = NT * 2 <= 32 ? 32 : (NT * 2 <= 64 ? 64 : (NT * 2 <= 128 ? 128 : (NT * 2 <= 256 ? 256 : 512)));
-    static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+    static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ + VEC_SMEM;
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -144,6 +148,14 @@ __host__ __device__ constexpr uint32_t instr_desc(int n)
     return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
+__device__ __forceinline__ void stage_channel_vectors(float *s_bias, float *s_slope, const float *bias, const float *slope, int Co)
+{
+    for (int i = threadIdx.x; i < MAX_CO_STAGED; i += blockDim.x) {
+        s_bias[i] = (bias != nullptr && i < Co) ? bias[i] : 0.f;
+        s_slope[i] = (slope != nullptr && i < Co) ? slope[i] : 1.f;
+    }
+}
+
 struct Tile {
     long long plane;
     int y0, x0, n0;
@@ -165,6 +177,69 @@ __device__ __forceinline__ bool tile_live(const TcParams &p, const Tile &t)
     return t.x0 < p.wl_out[(int)(t.plane % p.npart)];
 }
 
+
+// One output pixel (= one TMEM lane) of a finished accumulator tile: TMEM -> registers -> bias, PReLU / sigmoid, gate,
+// residual, invalid-column zeroing -> 128-bit NHWC stores.  `taddr` = TMEM address of this warp's lane quadrant and of
+// the accumulator stage's first column.  `bias` / `slope` point to the per-channel vectors staged in SHARED memory
+// (broadcast LDS; the global copies would be re-fetched from L2 after every cluster-scope acquire, which
+// invalidates L1 - that made the first pair kernel epilogue-bound).
+template <int NT>
+__device__ __forceinline__ void epilogue_pixel(const TcParams &p, long long plane, int oy, int ox, int n0, bool live, bool in_plane,
+                                               bool valid, uint32_t taddr0, const float *__restrict__ bias,
+                                               const float *__restrict__ slope, const float *__restrict__ mul,
+                                               const float *__restrict__ residual, float *__restrict__ y)
+{
+    const int nco = min(NT, p.Co - n0 * NT);       // multiple of 4
+    const int cbase = n0 * NT;
+    float *yp = y + (((plane * p.out_rows + oy + p.out_y0) * (long long)p.out_pitch) + ox + p.out_x0) * p.Co + cbase;
+    const long long aoff = (((plane * p.aux_rows + oy + p.aux_y0) * (long long)p.aux_pitch) + ox + p.aux_x0) * p.Co + cbase;
+    constexpr int STEP = NT >= 32 ? 32 : 16;
+#pragma unroll 1
+    for (int c0 = 0; c0 < NT; c0 += STEP) {
+        uint32_t v[STEP];
+        if (live) {
+            const uint32_t taddr = taddr0 + (uint32_t)c0;
+            if constexpr (STEP == 32) tmem_ld32(taddr, v);
+            else tmem_ld16(taddr, v);
+            tmem_wait_ld();
+        }
+        if (in_plane) {
+#pragma unroll
+            for (int j = 0; j < STEP; j += 4) {
+                const int co = c0 + j;
+                if (co >= nco) break;
+                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) {
+                    r = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    if (bias) {
+                        const float4 b4 = *reinterpret_cast<const float4 *>(bias + cbase + co);
+                        r.x = __fadd_rn(r.x, b4.x); r.y = __fadd_rn(r.y, b4.y); r.z = __fadd_rn(r.z, b4.z); r.w = __fadd_rn(r.w, b4.w);
+                    }
+                    if (p.act == 1) {
+                        const float4 s4 = *reinterpret_cast<const float4 *>(slope + cbase + co);
+                        if (r.x < 0.f) r.x = __fmul_rn(r.x, s4.x);
+                        if (r.y < 0.f) r.y = __fmul_rn(r.y, s4.y);
+                        if (r.z < 0.f) r.z = __fmul_rn(r.z, s4.z);
+                        if (r.w < 0.f) r.w = __fmul_rn(r.w, s4.w);
+                    } else if (p.act == 2) {
+                        r.x = 1.0f / (1.0f + expf(-r.x)); r.y = 1.0f / (1.0f + expf(-r.y));
+                        r.z = 1.0f / (1.0f + expf(-r.z)); r.w = 1.0f / (1.0f + expf(-r.w));
+                    }
+                    if (mul) {
+                        const float4 m4 = __ldg(reinterpret_cast<const float4 *>(mul + aoff + co));
+                        r.x = __fmul_rn(r.x, m4.x); r.y = __fmul_rn(r.y, m4.y); r.z = __fmul_rn(r.z, m4.z); r.w = __fmul_rn(r.w, m4.w);
+                    }
+                    if (residual) {
+                        const float4 a4 = __ldg(reinterpret_cast<const float4 *>(residual + aoff + co));
+                        r.x = __fadd_rn(a4.x, r.x); r.y = __fadd_rn(a4.y, r.y); r.z = __fadd_rn(a4.z, r.z); r.w = __fadd_rn(a4.w, r.w);
+                    }
+                }
+                *reinterpret_cast<float4 *>(yp + co) = r;
+            }
+        }
+    }
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                   const __grid_constant__ CUtensorMap map_w, TcParams p,
@@ -182,6 +257,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     uint64_t *acc_full = empty_bar + C::STAGES;     // [2]
     uint64_t *acc_empty = acc_full + 2;             // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    float *s_bias = reinterpret_cast<float *>(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256);
+    float *s_slope = s_bias + MAX_CO_STAGED;
+    stage_channel_vectors(s_bias, s_slope, bias, slope, p.Co);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -217,9 +295,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 Tile tl = decode_tile(p, t);
                 if (!tile_live(p, tl)) continue;
+                int tap = 0, kb = 0, ky = 0, kx = 0;
                 for (int it = 0; it < iters; it++) {
-                    const int tap = it / kblocks, kb = it % kblocks;
-                    const int ky = tap / p.k, kx = tap % p.k;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char *sa = stage_base + (size_t)stage * C::STAGE_BYTES;
                     unsigned char *sb = sa + A_STAGE_BYTES;
@@ -227,43 +304,49 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     tma_load_4d(sa, &map_x, &full_bar[stage], kb * BLOCK_K, tl.x0 * p.stride + kx, tl.y0 * p.stride + ky, (int)tl.plane);
                     tma_load_3d(sb, &map_w, &full_bar[stage], kb * BLOCK_K, tl.n0 * NT, tap);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (++kb == kblocks) {
+                        kb = 0; ++tap;
+                        if (++kx == p.k) { kx = 0; ++ky; }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================================================================================== MMA issuer
-        int stage = 0;
-        uint32_t phase = 0;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        constexpr uint32_t idesc = instr_desc(NT);
-        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            Tile tl = decode_tile(p, t);
-            if (!tile_live(p, tl)) continue;
-            mbar_wait(&acc_empty[acc], acc_phase ^ 1);        // epilogue has drained this accumulator stage
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + acc * NT;
-            for (int it = 0; it < iters; it++) {
-                mbar_wait(&full_bar[stage], phase);
+        // one thread runs the whole loop; descriptors are `stage base + constant` (see conv_pair_kernel)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            constexpr uint32_t idesc = instr_desc(NT);
+            const uint64_t desc_hi = smem_desc(0, 16, 1024) & 0xFFFFFFFF00000000ull;
+            const uint32_t lo0 = (smem_u32(stage_base) >> 4) & 0x3fff;
+            for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                Tile tl = decode_tile(p, t);
+                if (!tile_live(p, tl)) continue;
+                mbar_wait(&acc_empty[acc], acc_phase ^ 1);        // epilogue has drained this accumulator stage
                 tc_fence_after();
-                if (lane == 0) {          // one thread issues the MMAs and, below, the commits that track them
-                    const uint32_t sa = smem_u32(stage_base + (size_t)stage * C::STAGE_BYTES);
-                    const uint32_t sb = sa + A_STAGE_BYTES;
+                const uint32_t tmem_d = tmem_base + acc * NT;
+                for (int it = 0; it < iters; it++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_lo = lo0 + (uint32_t)stage * (C::STAGE_BYTES >> 4);
+                    const uint32_t b_lo = a_lo + (A_STAGE_BYTES >> 4);
 #pragma unroll
                     for (int kk = 0; kk < BLOCK_K / UMMA_K; kk++) {
                         // both operands K-major SWIZZLE_128B: 8 tf32 = 32 B further inside the 128 B row per MMA,
                         // 8-row groups (one swizzle atom) 1024 B apart
-                        const uint64_t ad = smem_desc(sa + kk * UMMA_K * 4, 16, 1024);
-                        const uint64_t bd = smem_desc(sb + kk * UMMA_K * 4, 16, 1024);
+                        const uint64_t ad = desc_hi | (uint64_t)(a_lo + (uint32_t)((kk * UMMA_K * 4) >> 4));
+                        const uint64_t bd = desc_hi | (uint64_t)(b_lo + (uint32_t)((kk * UMMA_K * 4) >> 4));
                         umma_tf32(tmem_d, ad, bd, idesc, (it | kk) != 0);
                     }
+                    umma_commit(&empty_bar[stage]);               // smem slot free once these MMAs are done
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (lane == 0) umma_commit(&empty_bar[stage]);      // smem slot free once these MMAs are done
-                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                umma_commit(&acc_full[acc]);                      // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (lane == 0) umma_commit(&acc_full[acc]);             // accumulator complete -> epilogue
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // ===================================================================================== epilogue warps
@@ -284,55 +367,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 mbar_wait(&acc_full[acc], acc_phase);
                 tc_fence_after();
             }
-            const int nco = min(NT, p.Co - tl.n0 * NT);       // multiple of 4
-            const int cbase = tl.n0 * NT;
-            float *yp = y + (((tl.plane * p.out_rows + oy + p.out_y0) * (long long)p.out_pitch) + ox + p.out_x0) * p.Co + cbase;
-            const long long aoff = (((tl.plane * p.aux_rows + oy + p.aux_y0) * (long long)p.aux_pitch) + ox + p.aux_x0) * p.Co + cbase;
-            constexpr int STEP = NT >= 32 ? 32 : 16;
-#pragma unroll 1
-            for (int c0 = 0; c0 < NT; c0 += STEP) {
-                uint32_t v[STEP];
-                if (live) {
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + c0);
-                    if constexpr (STEP == 32) tmem_ld32(taddr, v);
-                    else tmem_ld16(taddr, v);
-                    tmem_wait_ld();
-                }
-                if (in_plane) {
-#pragma unroll
-                    for (int j = 0; j < STEP; j += 4) {
-                        const int co = c0 + j;
-                        if (co >= nco) break;
-                        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (valid) {
-                            r = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                            if (bias) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + cbase + co));
-                                r.x = __fadd_rn(r.x, b4.x); r.y = __fadd_rn(r.y, b4.y); r.z = __fadd_rn(r.z, b4.z); r.w = __fadd_rn(r.w, b4.w);
-                            }
-                            if (p.act == 1) {
-                                const float4 s4 = __ldg(reinterpret_cast<const float4 *>(slope + cbase + co));
-                                if (r.x < 0.f) r.x = __fmul_rn(r.x, s4.x);
-                                if (r.y < 0.f) r.y = __fmul_rn(r.y, s4.y);
-                                if (r.z < 0.f) r.z = __fmul_rn(r.z, s4.z);
-                                if (r.w < 0.f) r.w = __fmul_rn(r.w, s4.w);
-                            } else if (p.act == 2) {
-                                r.x = 1.0f / (1.0f + expf(-r.x)); r.y = 1.0f / (1.0f + expf(-r.y));
-                                r.z = 1.0f / (1.0f + expf(-r.z)); r.w = 1.0f / (1.0f + expf(-r.w));
-                            }
-                            if (mul) {
-                                const float4 m4 = __ldg(reinterpret_cast<const float4 *>(mul + aoff + co));
-                                r.x = __fmul_rn(r.x, m4.x); r.y = __fmul_rn(r.y, m4.y); r.z = __fmul_rn(r.z, m4.z); r.w = __fmul_rn(r.w, m4.w);
-                            }
-                            if (residual) {
-                                const float4 a4 = __ldg(reinterpret_cast<const float4 *>(residual + aoff + co));
-                                r.x = __fadd_rn(a4.x, r.x); r.y = __fadd_rn(a4.y, r.y); r.z = __fadd_rn(a4.z, r.z); r.w = __fadd_rn(a4.w, r.w);
-                            }
-                        }
-                        *reinterpret_cast<float4 *>(yp + co) = r;
-                    }
-                }
-            }
+            epilogue_pixel<NT>(p, tl.plane, oy, ox, tl.n0, live, in_plane, valid, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT),
+                               bias ? s_bias : nullptr, s_slope, mul, residual, y);
             if (live) {
                 tc_fence_before();
                 __syncwarp();
@@ -346,6 +382,307 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+
+// ================================================================================================ 3x3 stride-1, CTA pairs
+// conv_pair_kernel: the 3x3 / stride-1 layers (the bulk of the transforms' FLOPs) on `cta_group::2` MMAs.
+//
+// The single-CTA kernel above is bound by L2 -> shared-memory bandwidth, not by the tensor pipe (ncu, profiles/r1a_*:
+// tensor pipe 44 % active, 2.2 MB of operand traffic per 128-pixel tile against ~43 B/clk/SM of L2 bandwidth).  Two
+// changes cut the traffic 2.3x:
+//   * a CTA pair (cluster of 2, one tile row each) shares every weight block: each CTA stages only HALF of the
+//     N = NT weight rows and `tcgen05.mma.cta_group::2` (M = 256) reads both halves;
+//   * the activation tile is staged ONCE per 32-channel block as a halo tile [3 rows][130 pixels][32 ch] (one TMA
+//     box, SWIZZLE_128B) and the nine filter taps are nine shared-memory DESCRIPTORS into it (start address shifted
+//     by (ky*130 + kx) pixel rows of 128 B) instead of nine TMA loads.
+// Pipelines: A halo ring (2 stages), B ring (8 stages of NT/2 x 32), TMEM accumulator ring (2 stages) - all mbarrier
+// based; full barriers live in the leader CTA (rank 0), whose warp 1 issues the MMAs for the pair; empty / accumulator
+// barriers are signalled in both CTAs by multicast commits.
+constexpr int HALO_W = BLOCK_M + 2;                         // pixels per halo-tile row
+constexpr int A2_BYTES = 3 * HALO_W * BLOCK_K * 4;          // 49,920 B landed by one TMA box
+constexpr int A2_STAGE = (A2_BYTES + 1023) / 1024 * 1024;   // 50,176 B (swizzle atoms stay 1024-aligned)
+constexpr int A2_STAGES = 2;
+constexpr int B2_STAGES = 8;
+
+template <int NT>
+struct Cfg2 {
+    static constexpr int B_HALF = NT / 2 * BLOCK_K * 4;     // bytes of weights staged per CTA and (tap, k-block)
+    static constexpr int B_STAGE = B_HALF < 1024 ? 1024 : B_HALF;
+    static constexpr int TMEM_COLS = Cfg<NT>::TMEM_COLS;
+    static constexpr size_t SMEM = 1024 + (size_t)A2_STAGES * A2_STAGE + (size_t)B2_STAGES * B_STAGE + 512 + VEC_SMEM;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the same barrier / buffer in the pair's leader CTA (rank 0): clear the peer bit of the shared::cluster address
+__device__ __forceinline__ uint32_t leader_addr(const void *p)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_u32(p)));
+    return r;
+}
+
+__device__ __forceinline__ void tma2_load_4d(void *dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(void *dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t *dst_smem, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_tf32_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.eq.b32 p, 0, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc)
+        : "memory");
+}
+// arrive (once all MMAs issued so far are complete) on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITC_%=:\n"
+        "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONEC_%=;\n"
+        "bra WAITC_%=;\n"
+        "DONEC_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__host__ __device__ constexpr uint32_t instr_desc2(int n)     // as instr_desc, M = 256 across the CTA pair
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+struct PairTile {
+    long long plane;
+    int y0, x0, n0;       // y0 = first of the pair's two rows
+};
+// pair tiles: n-tile fastest, then 128-column tile, then row pair, then plane
+__device__ __forceinline__ PairTile decode_pair(const TcParams &p, long long t)
+{
+    PairTile r;
+    r.n0 = (int)(t % p.n_tiles); t /= p.n_tiles;
+    r.x0 = (int)(t % p.tiles_x) * BLOCK_M; t /= p.tiles_x;
+    r.y0 = (int)(t % p.tiles_y) * 2; t /= p.tiles_y;
+    r.plane = t;
+    return r;
+}
+
+template <int NT, bool DBG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+    conv_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, TcParams p,
+                     const float *__restrict__ bias, const float *__restrict__ slope, const float *__restrict__ mul,
+                     const float *__restrict__ residual, float *__restrict__ y)
+{
+    using C = Cfg2<NT>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *a_base = smem;
+    unsigned char *b_base = smem + (size_t)A2_STAGES * A2_STAGE;
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(b_base + (size_t)B2_STAGES * C::B_STAGE);
+    uint64_t *a_empty = a_full + A2_STAGES;
+    uint64_t *b_full = a_empty + A2_STAGES;
+    uint64_t *b_empty = b_full + B2_STAGES;
+    uint64_t *acc_full = b_empty + B2_STAGES;       // [2]
+    uint64_t *acc_empty = acc_full + 2;             // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    float *s_bias = reinterpret_cast<float *>(b_base + (size_t)B2_STAGES * C::B_STAGE + 512);
+    float *s_slope = s_bias + MAX_CO_STAGED;
+    stage_channel_vectors(s_bias, s_slope, bias, slope, p.Co);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const long long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_x);
+        prefetch_tmap(&map_w);
+        for (int s = 0; s < A2_STAGES; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < B2_STAGES; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], 8);           // four epilogue warps in each CTA of the pair
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc2(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int kblocks = p.Ci / BLOCK_K;
+
+    if (warp == 0) {
+        // ===================================================================================== TMA producer (both CTAs)
+        if (lane == 0) {
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            for (long long t = cluster_id; t < p.total_tiles; t += n_clusters) {
+                PairTile tl = decode_pair(p, t);
+                if (tl.x0 >= p.wl_out[(int)(tl.plane % p.npart)]) continue;
+                for (int kb = 0; kb < kblocks; kb++) {
+                    mbar_wait(&a_empty[sa], pa ^ 1);
+                    if (rank == 0) mbar_expect_tx(&a_full[sa], 2 * A2_BYTES);
+                    // halo tile: input rows y .. y+2, columns x0 .. x0+129 of the (pre-padded) plane, 32 channels
+                    tma2_load_4d(a_base + (size_t)sa * A2_STAGE, &map_x, leader_addr(&a_full[sa]), kb * BLOCK_K, tl.x0, tl.y0 + (int)rank,
+                                 (int)tl.plane);
+                    if (++sa == A2_STAGES) { sa = 0; pa ^= 1; }
+                    for (int tap = 0; tap < 9; tap++) {
+                        mbar_wait(&b_empty[sb], pb ^ 1);
+                        if (rank == 0) mbar_expect_tx(&b_full[sb], 2 * C::B_HALF);
+                        tma2_load_3d(b_base + (size_t)sb * C::B_STAGE, &map_w, leader_addr(&b_full[sb]), kb * BLOCK_K,
+                                     tl.n0 * NT + (int)rank * (NT / 2), tap);
+                        if (++sb == B2_STAGES) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================================== MMA issuer (leader CTA)
+        // ONE thread runs the whole loop (no per-MMA elect / reconvergence), the tap loop is fully unrolled so every
+        // descriptor is `stage base + compile-time constant`: the issue loop, not L2 or the tensor pipe, was the
+        // limiter of the first version (ncu source page, profiles/r1b_*).
+        if (rank == 0 && lane == 0) {
+            int sa = 0, sb = 0, acc = 0;
+            uint32_t pa = 0, pb = 0, acc_phase = 0;
+            constexpr uint32_t idesc = instr_desc2(NT);
+            const uint64_t desc_hi = smem_desc(0, 16, 1024) & 0xFFFFFFFF00000000ull;
+            const uint32_t a_lo0 = (smem_u32(a_base) >> 4) & 0x3fff;
+            const uint32_t b_lo0 = (smem_u32(b_base) >> 4) & 0x3fff;
+            long long w_acc = 0, w_a = 0, w_b = 0;
+            const long long t_begin = DBG ? clock64() : 0;
+            for (long long t = cluster_id; t < p.total_tiles; t += n_clusters) {
+                PairTile tl = decode_pair(p, t);
+                if (tl.x0 >= p.wl_out[(int)(tl.plane % p.npart)]) continue;
+                long long t0 = DBG ? clock64() : 0;
+                mbar_wait_cluster(&acc_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                long long t1 = DBG ? clock64() : 0;
+                w_acc += t1 - t0;
+                const uint32_t tmem_d = tmem_base + acc * NT;
+                for (int kb = 0; kb < kblocks; kb++) {
+                    if (DBG) t0 = clock64();
+                    mbar_wait(&a_full[sa], pa);
+                    if (DBG) t1 = clock64();
+                    w_a += t1 - t0;
+                    const uint32_t a_lo = a_lo0 + (uint32_t)sa * (A2_STAGE >> 4);
+#pragma unroll
+                    for (int tap = 0; tap < 9; tap++) {
+                        if (DBG) t0 = clock64();
+                        mbar_wait(&b_full[sb], pb);
+                        tc_fence_after();
+                        if (DBG) t1 = clock64();
+                        w_b += t1 - t0;
+                        const uint32_t b_lo = b_lo0 + (uint32_t)sb * (C::B_STAGE >> 4);
+                        const int r0 = (tap / 3) * HALO_W + (tap % 3);          // compile-time after unrolling
+#pragma unroll
+                        for (int kk = 0; kk < BLOCK_K / UMMA_K; kk++) {
+                            const uint64_t ad = desc_hi | (uint64_t)(a_lo + (uint32_t)((r0 * BLOCK_K * 4 + kk * UMMA_K * 4) >> 4));
+                            const uint64_t bd = desc_hi | (uint64_t)(b_lo + (uint32_t)((kk * UMMA_K * 4) >> 4));
+                            if (tap == 0 && kk == 0) umma2_tf32(tmem_d, ad, bd, idesc, kb != 0);
+                            else umma2_tf32_acc(tmem_d, ad, bd, idesc);
+                        }
+                        umma2_commit(&b_empty[sb]);
+                        if (++sb == B2_STAGES) { sb = 0; pb ^= 1; }
+                    }
+                    umma2_commit(&a_empty[sa]);
+                    if (++sa == A2_STAGES) { sa = 0; pa ^= 1; }
+                }
+                umma2_commit(&acc_full[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            if (DBG && p.dbg) {
+                long long *d = p.dbg + 4 * cluster_id;
+                d[0] = clock64() - t_begin; d[1] = w_acc; d[2] = w_a; d[3] = w_b;
+            }
+        }
+    } else {
+        // ===================================================================================== epilogue warps (both CTAs)
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long long t = cluster_id; t < p.total_tiles; t += n_clusters) {
+            PairTile tl = decode_pair(p, t);
+            const int wl = p.wl_out[(int)(tl.plane % p.npart)];
+            const int oy = tl.y0 + (int)rank;
+            const int ox = tl.x0 + m;
+            const bool in_plane = oy < p.Ho && ox < p.Wo;
+            const bool valid = in_plane && ox < wl;
+            const bool live = tl.x0 < wl;
+            if (live) {
+                mbar_wait(&acc_full[acc], acc_phase);
+                tc_fence_after();
+            }
+            epilogue_pixel<NT>(p, tl.plane, oy, ox, tl.n0, live, in_plane, valid, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT),
+                               bias ? s_bias : nullptr, s_slope, mul, residual, y);
+            if (live) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(leader_addr(&acc_empty[acc]));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, C::TMEM_COLS);
     }
 }
 
@@ -435,6 +772,41 @@ static int launch_tc(const CUtensorMap &mx, const CUtensorMap &mw, const TcParam
     return PCX_OK;
 }
 
+
+template <int NT, bool DBG = false>
+static int launch_pair(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, const float *bias, const float *slope,
+                       const float *mul, const float *residual, float *y, cudaStream_t s)
+{
+    using C = Cfg2<NT>;
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+        PCX_CUDA(cudaFuncSetAttribute(conv_pair_kernel<NT, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(pcx_sm_count() / 2 * 2);
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = C::SMEM;
+        int n = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, conv_pair_kernel<NT, DBG>, &cfg);
+        if (e != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = pcx_sm_count() / 2; }
+        max_clusters = n;
+    }
+    long long clusters = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;
+    conv_pair_kernel<NT, DBG><<<(unsigned)(2 * clusters), NUM_THREADS, C::SMEM, s>>>(mx, mw, p, bias, slope, mul, residual, y);
+    PCX_LAUNCHED();
+    return PCX_OK;
+}
+
+static int pair_mode()
+{
+    // PCX_TC_PAIR: 0 = never use the CTA-pair kernel, 1 (default) = 3x3 stride-1 layers with Wo >= 64
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("PCX_TC_PAIR");
+        mode = e ? atoi(e) : 1;
+    }
+    return mode;
+}
+
 int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w, const float *d_bias, const float *d_slope,
                   const float *d_mul, const float *d_residual, float *d_y, void *stream)
 {
@@ -443,7 +815,7 @@ int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w,
     const int nt = n_tile_for(d.Co);
     PCX_REQUIRE(nt != 0 && d.Ci % BLOCK_K == 0, "tensor-core conv needs Co <= 16 or a multiple of 96 and Ci a multiple of 32 (Co=%d Ci=%d); use impl=1", d.Co, d.Ci);
     PCX_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_y) & 15) == 0, "tensor-core conv needs 16-byte aligned NHWC buffers");
-    PCX_REQUIRE(d.Co % 4 == 0, "tensor-core conv needs Co %% 4 == 0 (got %d)", d.Co);
+    PCX_REQUIRE(d.Co % 4 == 0 && d.Co <= MAX_CO_STAGED, "tensor-core conv needs Co %% 4 == 0 and Co <= %d (got %d)", MAX_CO_STAGED, d.Co);
     const int bw = d.Wo >= 512 ? 128 : (d.Wo >= 256 ? 64 : 32);
     const int bh = BLOCK_M / bw;
     EncodeTiledFn enc = encode_tiled();
@@ -476,9 +848,22 @@ int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w,
         if (rc < 0) return (int)rc;
     }
 
+    const bool pair = pair_mode() != 0 && d.k == 3 && d.stride == 1 && d.Wo >= 64;
+
     // ---- tensor maps
     CUtensorMap mx, mw;
-    {
+    if (pair) {
+        // halo tile of the CTA-pair kernel: 32 channels x 130 columns x 3 rows
+        const long long planes = (long long)d.N * d.npart;
+        cuuint64_t dims[4] = {(cuuint64_t)d.Ci, (cuuint64_t)d.in_pitch, (cuuint64_t)d.Hi, (cuuint64_t)planes};
+        cuuint64_t strides[3] = {(cuuint64_t)d.Ci * 4, (cuuint64_t)d.Ci * d.in_pitch * 4, (cuuint64_t)d.Ci * d.in_pitch * d.Hi * 4};
+        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)HALO_W, 3, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(d_x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        PCX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(halo tile) failed with %d", (int)r);
+    } else {
         const long long planes = (long long)d.N * d.npart;
         cuuint64_t dims[4] = {(cuuint64_t)d.Ci, (cuuint64_t)d.in_pitch, (cuuint64_t)d.Hi, (cuuint64_t)planes};
         cuuint64_t strides[3] = {(cuuint64_t)d.Ci * 4, (cuuint64_t)d.Ci * d.in_pitch * 4, (cuuint64_t)d.Ci * d.in_pitch * d.Hi * 4};
@@ -492,7 +877,7 @@ int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w,
     {
         cuuint64_t dims[3] = {(cuuint64_t)d.Ci, (cuuint64_t)co_pad, (cuuint64_t)(d.k * d.k)};
         cuuint64_t strides[2] = {(cuuint64_t)d.Ci * 4, (cuuint64_t)d.Ci * co_pad * 4};
-        cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)nt, 1};
+        cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)(pair ? nt / 2 : nt), 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, packed, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -513,6 +898,36 @@ int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w,
     p.total_tiles = (long long)p.planes * p.tiles_y * p.tiles_x * p.n_tiles;
     for (int i = 0; i < PCX_MAX_PART; i++) p.wl_out[i] = d.wl_out[i];
 
+    p.dbg = nullptr;
+    if (pair) {
+        static long long *dbg = nullptr;
+        if (getenv("PCX_TC_DEBUG")) {
+            if (!dbg) { cudaMalloc(&dbg, 4 * 128 * sizeof(long long)); }
+            p.dbg = dbg;
+        }
+        p.bw = BLOCK_M; p.bh = 1;
+        p.tiles_x = (d.Wo + BLOCK_M - 1) / BLOCK_M;
+        p.tiles_y = (d.Ho + 1) / 2;
+        p.total_tiles = (long long)p.planes * p.tiles_y * p.tiles_x * p.n_tiles;
+        if (p.dbg) {
+            int rc = nt == 192 ? launch_pair<192, true>(mx, mw, p, d_bias, d_slope, d_mul, d_residual, d_y, s)
+                               : (nt == 96 ? launch_pair<96, true>(mx, mw, p, d_bias, d_slope, d_mul, d_residual, d_y, s)
+                                           : launch_pair<16, true>(mx, mw, p, d_bias, d_slope, d_mul, d_residual, d_y, s));
+            static int printed = 0;
+            if (printed++ < 3) {
+                long long h[4 * 74];
+                cudaStreamSynchronize(s);
+                cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+                for (int c = 0; c < 74; c += 18)
+                    fprintf(stderr, "[pcx dbg] cluster %2d: total %lld clk, wait acc_empty %lld, a_full %lld, b_full %lld\n", c, h[4 * c], h[4 * c + 1],
+                            h[4 * c + 2], h[4 * c + 3]);
+            }
+            return rc;
+        }
+        if (nt == 192) return launch_pair<192>(mx, mw, p, d_bias, d_slope, d_mul, d_residual, d_y, s);
+        if (nt == 96) return launch_pair<96>(mx, mw, p, d_bias, d_slope, d_mul, d_residual, d_y, s);
+        return launch_pair<16>(mx, mw, p, d_bias, d_slope, d_mul, d_residual, d_y, s);
+    }
     if (nt == 192) return launch_tc<192>(mx, mw, p, d_bias, d_slope, d_mul, d_residual, d_y, s);
     if (nt == 96) return launch_tc<96>(mx, mw, p, d_bias, d_slope, d_mul, d_residual, d_y, s);
     return launch_tc<16>(mx, mw, p, d_bias, d_slope, d_mul, d_residual, d_y, s);
