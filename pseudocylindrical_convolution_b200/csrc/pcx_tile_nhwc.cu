@@ -16,6 +16,7 @@
 // (channels for the tiles, longitude for the ERP image), so both sides of the transpose move full 128-byte lines.
 // Shared-memory pitches are odd so the transposed reads are bank-conflict free.
 #include "pcx_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -49,6 +50,8 @@ __device__ __forceinline__ void cp_async_wait_all()
 struct SlicePadParams {
     int N, C, h, W, pad, out_pitch;
     int xb[PCX_MAX_PART];   // logical tile columns per CTA, per band (narrow polar bands span more ERP columns per column)
+    int xoff[PCX_MAX_PART + 1];   // prefix sum of the bands' column-chunk counts (persistent kernel's super-tile index)
+    int xtotal;
     int xchunks;       // column chunks per row (max over bands)
     int cchunks;
     int scap;          // shared-memory row capacity in floats (odd pitch = scap | 1)
@@ -214,6 +217,230 @@ __global__ void __launch_bounds__(NTHREADS) slice_pad_nhwc_kernel(const float *_
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ slice + pad, TMA-staged
+// Second version of the fused gather: persistent, warp-specialised, TMA-pipelined.
+// The first one (above, kept for widths that are not a multiple of 4) is one small CTA per tile: half of its
+// instructions are 4-byte cp.async staging and every CTA pays the whole table-load -> stage -> compute -> store latency
+// chain with little memory traffic in flight (55 % of the HBM roofline; ncu, profiles/r1a_*).  Here
+//   * CTAs are persistent (2 per SM) and walk "super-tiles" = (tile row y, band g, column chunk); inside one the
+//     geometry and the per-column recipes are loop invariants and the CTA streams all images x 32-channel chunks;
+//   * warp 0 is the producer: the circular span of every channel row is staged by 1-D bulk TMA copies
+//     (`cp.async.bulk`, 16-byte aligned, one lane per channel row, completion on an mbarrier) into a 3-stage ring,
+//     so ~120 KB of loads are in flight per SM while the eight consumer warps work;
+//   * consumers: compute with lanes along the tile's x (each thread owns ONE column: its recipe stays in registers),
+//     taps read from s_in[c][o..o+3], result to s_out[x][c] (pitch 33); then store with lanes along channels,
+//     s_out[x][lane] -> 128-byte channels-last segments.  Both sides of the transpose are bank-conflict free.
+constexpr int SROW = 160;          // floats per staged channel row: span (<= 152) + alignment slack, multiple of 4
+constexpr int SP_STAGES = 3;
+constexpr int SP_THREADS = 32 + 256;
+constexpr size_t SP_SMEM = (size_t)SP_STAGES * CB * SROW * 4 + 2 * XB_MAX * (CB + 1) * 4 + 64;
+
+struct SuperGeom {
+    int g, y, x0, x1, wl, sb, erow, hr, wsrc, base_al, span_al, n1;
+};
+
+__device__ __forceinline__ SuperGeom super_geometry(i64 s, const Bands &bands, const SlicePadParams &P, const int *__restrict__ stab,
+                                                    const int *__restrict__ hband, const int *__restrict__ hrow,
+                                                    const int *__restrict__ hcol)
+{
+    SuperGeom G;
+    const int W = P.W, h = P.h, pad = P.pad;
+    G.y = (int)(s / P.xtotal);
+    const int r = (int)(s % P.xtotal);
+    int g = 0;
+    while (g + 1 < bands.npart && P.xoff[g + 1] <= r) g++;
+    G.g = g;
+    G.wl = bands.wl[g];
+    G.x0 = (r - P.xoff[g]) * P.xb[g];
+    G.x1 = min(G.x0 + P.xb[g], G.wl);
+    G.hr = -1;
+    if (G.y >= pad && G.y < pad + h) {
+        G.sb = g;
+        G.erow = g * h + (G.y - pad);
+    } else {
+        const int sd = G.y < pad ? 0 : 1, rr = G.y < pad ? G.y : G.y - pad - h;
+        G.hr = (g * 2 + sd) * pad + rr;
+        G.sb = hband[G.hr];
+        G.erow = G.sb * h + hrow[G.hr];
+    }
+    G.wsrc = bands.wl[G.sb];
+    const int *tab = stab + (i64)G.sb * W;
+    int base = 0, span = W + 3;
+    if (W > P.scap) {
+        int first, last;
+        if (G.hr < 0) {
+            first = tab[G.x0];
+            last = tab[G.x1 - 1];
+        } else {
+            first = tab[hcol[(i64)G.hr * W + G.x0]];
+            const int q = hcol[(i64)G.hr * W + G.x1 - 1];
+            const int q1 = (q + 1 == G.wsrc) ? 0 : q + 1;
+            last = tab[q1];
+        }
+        base = wrap_mod(first - 1, W);
+        span = circ_dist(base, wrap_mod(last + 2, W), W) + 1;
+        if (span > P.scap) __trap();              // host sizing guarantees this cannot happen
+    }
+    G.base_al = base & ~3;
+    G.span_al = (span + (base - G.base_al) + 3) & ~3;          // <= SROW
+    G.n1 = min(G.span_al, W - G.base_al);                      // floats before the longitude wrap (multiple of 4)
+    return G;
+}
+
+__global__ void __launch_bounds__(SP_THREADS, 2) slice_pad_tma_kernel(const float *__restrict__ erp, float *__restrict__ out,
+                                                                   const int *__restrict__ stab, const float4 *__restrict__ swt,
+                                                                   const int *__restrict__ hband, const int *__restrict__ hrow,
+                                                                   const int *__restrict__ hcol, const float *__restrict__ htw,
+                                                                   Bands bands, SlicePadParams P)
+{
+    extern __shared__ __align__(128) unsigned char sp_smem[];
+    float *s_in = reinterpret_cast<float *>(sp_smem);                                              // [SP_STAGES][CB][SROW]
+    float *s_out = s_in + SP_STAGES * CB * SROW;                                                   // [2][XB_MAX][CB + 1]
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_out + 2 * XB_MAX * (CB + 1));                  // [SP_STAGES]
+    uint64_t *empty = full + SP_STAGES;                                                            // [SP_STAGES]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int npart = bands.npart;
+    const int W = P.W, h = P.h, pad = P.pad, C = P.C;
+    const int OH = h + 2 * pad;
+    const i64 n_super = (i64)OH * P.xtotal;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < SP_STAGES; i++) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 8);             // one arrival per consumer warp
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    int stage = 0;
+    uint32_t phase = 0;
+    if (warp == 0) {
+        // ===================================================================================== producer
+        for (i64 s = blockIdx.x; s < n_super; s += gridDim.x) {
+            const SuperGeom G = super_geometry(s, bands, P, stab, hband, hrow, hcol);
+            const int n2 = G.span_al - G.n1;
+            for (int n = 0; n < P.N; n++) {
+                for (int cc = 0; cc < P.cchunks; cc++) {
+                    const int c0 = cc * CB, nc = min(CB, C - c0);
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (lane == 0) mbar_expect_tx(&full[stage], (uint32_t)(nc * G.span_al * 4));
+                    __syncwarp();
+                    if (lane < nc) {
+                        const float *sr = erp + (((i64)n * C + c0 + lane) * (i64)(h * npart) + G.erow) * W;
+                        float *dr = s_in + ((size_t)stage * CB + lane) * SROW;
+                        bulk_g2s(dr, sr + G.base_al, (uint32_t)(G.n1 * 4), &full[stage]);
+                        if (n2 > 0) bulk_g2s(dr + G.n1, sr, (uint32_t)(n2 * 4), &full[stage]);
+                    }
+                    if (++stage == SP_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ========================================================================================= consumers (8 warps)
+    const int cw = warp - 1;
+    const int xi = (cw & 3) * 32 + lane;          // this thread's column inside the chunk
+    const int cg = (cw >> 2) * (CB / 2);          // and its 16-channel group
+    int buf = 0;
+    for (i64 s = blockIdx.x; s < n_super; s += gridDim.x) {
+        const SuperGeom G = super_geometry(s, bands, P, stab, hband, hrow, hcol);
+        const int nx = G.x1 - G.x0;
+        const int *tab = stab + (i64)G.sb * W;
+        const float4 *wtab = swt + (i64)G.sb * W;
+        float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa;
+        int oa = 0, ob = 0;
+        float t = 0.f;
+        if (xi < nx) {
+            const int x = G.x0 + xi;
+            if (G.hr < 0) {
+                wa = wtab[x];
+                const int o = tab[x] - 1 - G.base_al;
+                oa = o < 0 ? o + W : o;
+            } else {
+                const i64 e = (i64)G.hr * W + x;
+                const int q = hcol[e];
+                const int q1 = (q + 1 == G.wsrc) ? 0 : q + 1;
+                wa = wtab[q];
+                wb = wtab[q1];
+                int o = tab[q] - 1 - G.base_al;
+                oa = o < 0 ? o + W : o;
+                o = tab[q1] - 1 - G.base_al;
+                ob = o < 0 ? o + W : o;
+                t = htw[e];
+            }
+        }
+        for (int n = 0; n < P.N; n++) {
+            const i64 plane = (i64)n * npart + G.g;
+            for (int cc = 0; cc < P.cchunks; cc++) {
+                const int c0 = cc * CB, nc = min(CB, C - c0);
+                float *so = s_out + (size_t)buf * XB_MAX * (CB + 1);
+                const float *si = s_in + (size_t)stage * CB * SROW;
+                mbar_wait(&full[stage], phase);
+                if (xi < nx) {
+                    float *dst = so + xi * (CB + 1) + cg;
+                    if (G.hr < 0) {
+#pragma unroll
+                        for (int c = 0; c < CB / 2; c++) {
+                            const float *r = si + (cg + c) * SROW + oa;
+                            dst[c] = tap4_ref<true>(wa, r[0], r[1], r[2], r[3]);
+                        }
+                    } else {
+#pragma unroll 8
+                        for (int c = 0; c < CB / 2; c++) {
+                            const float *ra = si + (cg + c) * SROW + oa;
+                            const float *rb = si + (cg + c) * SROW + ob;
+                            const float a = tap4_ref<true>(wa, ra[0], ra[1], ra[2], ra[3]);
+                            const float b = tap4_ref<true>(wb, rb[0], rb[1], rb[2], rb[3]);
+                            dst[c] = lerp2_ref(a, b, t);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stage]);                 // this warp no longer reads the stage
+                if (++stage == SP_STAGES) { stage = 0; phase ^= 1; }
+                asm volatile("bar.sync 1, 256;" ::: "memory");             // s_out[buf] complete (consumer warps only)
+
+                // store: lanes along channels; the longitude wrap (pseudo_pad.cu:82-96) re-uses the staged results:
+                // left pad <- last `pad` columns, right pad <- first `pad` columns
+                float *orow = out + ((plane * OH + G.y) * (i64)P.out_pitch) * C + c0;
+                if (lane < nc) {
+                    // lean main loop (this loop was 38 % of the first TMA version's instructions): running pointers only
+                    float *op = orow + (i64)(pad + G.x0 + cw) * C + lane;
+                    const float *sp = so + cw * (CB + 1) + lane;
+                    const i64 ostep = (i64)8 * C;
+                    int i = cw;
+#pragma unroll 1
+                    for (; i + 24 < nx; i += 32, op += 4 * ostep, sp += 32 * (CB + 1)) {
+                        const float v0 = sp[0], v1 = sp[8 * (CB + 1)], v2 = sp[16 * (CB + 1)], v3 = sp[24 * (CB + 1)];
+                        op[0] = v0; op[ostep] = v1; op[2 * ostep] = v2; op[3 * ostep] = v3;
+                    }
+                    for (; i < nx; i += 8, op += ostep, sp += 8 * (CB + 1)) *op = *sp;
+                    // wrap columns: at most 2 * pad per row, only in the first / last chunk of the band
+                    if (G.x0 < pad || G.x1 > G.wl - pad) {
+                        for (int j = cw; j < 2 * pad; j += 8) {
+                            const int x = j < pad ? j : G.wl - 2 * pad + j;                 // source logical column
+                            if (x < G.x0 || x >= G.x1) continue;
+                            const int X = j < pad ? pad + G.wl + j : j - pad;               // destination physical column
+                            orow[(i64)X * C + lane] = so[(x - G.x0) * (CB + 1) + lane];
+                        }
+                    }
+                    if (P.zero_invalid) {
+                        // columns beyond the band (PseudoPad leaves them 0; pseudo_pad.cu:39-54), split over the row's chunks
+                        const int chunks = (G.wl + P.xb[G.g] - 1) / P.xb[G.g];
+                        const int zb = (P.out_pitch - G.wl - 2 * pad + chunks - 1) / chunks;
+                        const int X0 = G.wl + 2 * pad + (G.x0 / P.xb[G.g]) * zb, X1 = min(X0 + zb, P.out_pitch);
+                        for (int X = X0 + cw; X < X1; X += 8) orow[(i64)X * C + lane] = 0.f;
+                    }
+                }
+                buf ^= 1;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ uslice
 struct UsliceParams {
     int N, C, h, W;
@@ -337,8 +564,23 @@ int pcx_slice_pad_nhwc(const float *d_in, float *d_out, int N, int C, int H, int
     PCX_REQUIRE((i64)P.cchunks * (P.h + 2 * pad) <= 65535 && (i64)N * npart <= 65535, "grid too large");
     const dim3 grid(P.xchunks, P.cchunks * (P.h + 2 * pad), N * npart);
     const size_t smem = XB_MAX * sizeof(ColRecipe) + (size_t)CB * ((P.scap + 3) | 1) * sizeof(float);
-    slice_pad_nhwc_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(d_in, d_out, d_src, (const float4 *)d_wt, d_band,
-                                                                                     d_row, d_col, d_tw, b, P);
+    static const bool force_v1 = getenv("PCX_SLICE_V1") != nullptr;
+    P.xoff[0] = 0;
+    for (int i = 0; i < PCX_MAX_PART; i++) P.xoff[i + 1] = P.xoff[i] + (i < npart ? (wl[i] + P.xb[i] - 1) / P.xb[i] : 0);
+    P.xtotal = P.xoff[npart];
+    if (W % 4 == 0 && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 && !force_v1) {
+        static bool attr = false;
+        if (!attr) {
+            PCX_CUDA(cudaFuncSetAttribute(slice_pad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM));
+            attr = true;
+        }
+        const i64 n_super = (i64)(P.h + 2 * pad) * P.xtotal;
+        const i64 ctas = 2LL * pcx_sm_count();
+        slice_pad_tma_kernel<<<(unsigned)(n_super < ctas ? n_super : ctas), SP_THREADS, SP_SMEM, (cudaStream_t)stream>>>(
+            d_in, d_out, d_src, (const float4 *)d_wt, d_band, d_row, d_col, d_tw, b, P);
+    } else
+        slice_pad_nhwc_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(d_in, d_out, d_src, (const float4 *)d_wt, d_band,
+                                                                                         d_row, d_col, d_tw, b, P);
     PCX_LAUNCHED();
     return PCX_OK;
 }
