@@ -17,7 +17,7 @@
  * Parity pinning: the reference ships no golden vectors for this path.  The
  * oracle is pinned against outputs of the reference extension itself, built unmodified for sm_100
  * (oracle/build_ref.py -> oracle/_ref/PCONV_ref.so) and run on the B200 box; the vectors it produced
- * are committed under tests/golden/ with the script that made them (tests/golden/make_golden.py).
+ * are committed under tests/golden/ with the script that made them (tools/make_golden.py + tests/golden_cases.py).
  * Known, documented non-bit-exact spots versus the GPU: libm erff/expf (CUDA libdevice differs from
  * glibc by <= 1-2 ulp) - CDF entries may differ by +-1 count, quantiser step tables by <= 2 ulp.
  */
