@@ -107,6 +107,17 @@ int pcx_slice_pad_nhwc(const float *d_in, float *d_out, int N, int C, int H, int
  * [N*npart][in_rows][in_pitch][C] whose band data start at (in_y0, in_x0); out (N,C,h*npart,W) NCHW. */
 int pcx_uslice_nhwc(const float *d_in, float *d_out, int N, int C, int h, int W, int npart, int in_rows, int in_pitch,
                     int in_y0, int in_x0, const int *wl, const int *d_src, const float *d_wt, void *stream);
+/* B200-native channels-last companions of the tensor-core transforms:
+ * PseudoPadOp.forward as an in-place halo refresh of a channels-last tile buffer [N*npart][rows][pitch][C] whose band
+ * interiors start at (y0, x0) (y0, x0 >= pad); tables from pcx_halo_table(mode 0).  Same values as pcx_pad_fwd. */
+int pcx_halo_fill_nhwc(float *d_buf, int N, int C, int h, int W, int npart, int pad, const int *wl, const int *d_band,
+                       const int *d_row, const int *d_col, const float *d_tw, int rows, int pitch, int y0, int x0, void *stream);
+/* DtowOp.forward (d2w, stride 2; dtow_cuda.cu:38-55) on channels-last tiles: in [planes][in_rows][in_pitch][4*Co] window at
+ * (in_y0, in_x0) of extent h x W  ->  out [planes][out_rows][out_pitch][Co] window at (out_y0, out_x0) of extent 2h x 2W. */
+int pcx_dtow_nhwc(const float *d_in, float *d_out, int planes, int Co, int h, int W, int in_rows, int in_pitch, int in_y0,
+                  int in_x0, int out_rows, int out_pitch, int out_y0, int out_x0, void *stream);
+/* y = x * x elementwise (the x^2 operand of the GDN contraction, PseudoContextV2.py:207); n multiple of 4. */
+int pcx_square(const float *d_in, float *d_out, long long n, void *stream);
 /* PseudoFillOp.forward    (main.cpp:103-107 -> pseudo_fill_cuda.cu:46-61), in place. */
 int pcx_fill(float *d_data, int N, int C, int Hh, int Ww, int npart, int pad, int trim, const int *wl,
              float fvalue, void *stream);
@@ -131,7 +142,8 @@ int pcx_dquant_fwd(const float *d_sym, const float *d_theta, float *d_centres, f
  * Output (N*npart, Co, Ho, out_pitch) is written at row offset out_y0 / column offset out_x0 of each plane
  * (so a layer can write straight into the interior of the next layer's padded buffer).
  * Epilogue, in this order:  +bias ; act ; +residual ; zero columns >= wl_out[band] (PseudoFillV2).
- *   act: 0 none, 1 PReLU(d_slope per channel), 2 sigmoid.
+ *   act: 0 none, 1 PReLU(d_slope per channel), 2 sigmoid, 3 1/sqrt(.), 4 sqrt(.)  (3/4 with d_mul = x and a 1x1 conv of x^2
+ *        by gamma' + beta' are GDN / IGDN, PseudoContextV2.py:186-216; tensor-core impl only).
  * impl: 0 = tcgen05/TMEM implicit GEMM (TF32 operands, fp32 accumulate); tensors are NHWC
  *           (x [plane][Hi][in_pitch][Ci], y [plane][out_rows][out_pitch][Co], aux likewise), Ci % 32 == 0,
  *           Co <= 16 or Co % 96 == 0;
@@ -139,15 +151,16 @@ int pcx_dquant_fwd(const float *d_sym, const float *d_theta, float *d_centres, f
  *       2 = as 0, but d_w is already packed by pcx_conv_pack_weights (no per-call repack). */
 typedef struct pcx_conv_desc {
     int N, npart;            /* images, bands per image */
-    int Ci, Hi, in_pitch;    /* input planes: Hi rows of in_pitch floats */
+    int Ci, Hi, in_pitch;    /* input view: Hi rows of in_pitch pixels reachable from d_x */
     int Co, Ho, Wo;          /* output extent computed per plane */
     int out_rows, out_pitch; /* output plane geometry (rows x pitch) */
     int out_y0, out_x0;      /* where (0,0) of the result lands inside the output plane */
     int k, stride;           /* 1 or 3; 1 or 2 */
-    int act;                 /* 0 none, 1 PReLU, 2 sigmoid */
+    int act;                 /* 0 none, 1 PReLU, 2 sigmoid, 3 rsqrt, 4 sqrt */
     int impl;                /* 0 tensor core, 1 fp32 direct, 2 tensor core with pre-packed weights */
     int aux_rows, aux_pitch; /* geometry shared by the optional d_mul / d_residual planes (Co channels) */
     int aux_y0, aux_x0;
+    int in_plane_rows;       /* physical rows between consecutive input planes (0 = Hi); lets d_x point INTO a padded buffer */
     int wl_out[PCX_MAX_PART];/* valid output width per band (columns >= wl_out are written as 0) */
 } pcx_conv_desc;
 /* y = fill( residual + mul * act(conv(x) + bias) );  d_bias, d_slope, d_mul, d_residual may be NULL.

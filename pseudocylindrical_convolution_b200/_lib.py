@@ -20,7 +20,7 @@ class ConvDesc(C.Structure):
     """struct pcx_conv_desc (include/pcx.h)."""
     _fields_ = [(n, C.c_int) for n in (
         "N", "npart", "Ci", "Hi", "in_pitch", "Co", "Ho", "Wo", "out_rows", "out_pitch", "out_y0", "out_x0",
-        "k", "stride", "act", "impl", "aux_rows", "aux_pitch", "aux_y0", "aux_x0")] + [("wl_out", C.c_int * PCX_MAX_PART)]
+        "k", "stride", "act", "impl", "aux_rows", "aux_pitch", "aux_y0", "aux_x0", "in_plane_rows")] + [("wl_out", C.c_int * PCX_MAX_PART)]
 
 
 _P = C.c_void_p
@@ -47,6 +47,9 @@ PROTOTYPES = {
     "pcx_halo_fill": (_I, [_P, _I, _I, _I, _I, _I, _I, _IP, _P, _P, _P, _P, _I, _P]),
     "pcx_slice_pad_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _IP, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "pcx_uslice_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _IP, _P, _P, _P]),
+    "pcx_halo_fill_nhwc": (_I, [_P, _I, _I, _I, _I, _I, _I, _IP, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "pcx_dtow_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "pcx_square": (_I, [_P, _P, C.c_longlong, _P]),
     "pcx_fill": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _IP, _F, _P]),
     "pcx_dtow": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "pcx_quant_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _IP, _P]),

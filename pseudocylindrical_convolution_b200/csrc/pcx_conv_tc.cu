@@ -224,6 +224,10 @@ __device__ __forceinline__ void epilogue_pixel(const TcParams &p, long long plan
                     } else if (p.act == 2) {
                         r.x = 1.0f / (1.0f + expf(-r.x)); r.y = 1.0f / (1.0f + expf(-r.y));
                         r.z = 1.0f / (1.0f + expf(-r.z)); r.w = 1.0f / (1.0f + expf(-r.w));
+                    } else if (p.act == 3) {
+                        r.x = 1.0f / sqrtf(r.x); r.y = 1.0f / sqrtf(r.y); r.z = 1.0f / sqrtf(r.z); r.w = 1.0f / sqrtf(r.w);
+                    } else if (p.act == 4) {
+                        r.x = sqrtf(r.x); r.y = sqrtf(r.y); r.z = sqrtf(r.z); r.w = sqrtf(r.w);
                     }
                     if (mul) {
                         const float4 m4 = __ldg(reinterpret_cast<const float4 *>(mul + aoff + co));
@@ -849,6 +853,7 @@ int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w,
     }
 
     const bool pair = pair_mode() != 0 && d.k == 3 && d.stride == 1 && d.Wo >= 64;
+    const cuuint64_t plane_rows = (cuuint64_t)(d.in_plane_rows > 0 ? d.in_plane_rows : d.Hi);
 
     // ---- tensor maps
     CUtensorMap mx, mw;
@@ -856,7 +861,7 @@ int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w,
         // halo tile of the CTA-pair kernel: 32 channels x 130 columns x 3 rows
         const long long planes = (long long)d.N * d.npart;
         cuuint64_t dims[4] = {(cuuint64_t)d.Ci, (cuuint64_t)d.in_pitch, (cuuint64_t)d.Hi, (cuuint64_t)planes};
-        cuuint64_t strides[3] = {(cuuint64_t)d.Ci * 4, (cuuint64_t)d.Ci * d.in_pitch * 4, (cuuint64_t)d.Ci * d.in_pitch * d.Hi * 4};
+        cuuint64_t strides[3] = {(cuuint64_t)d.Ci * 4, (cuuint64_t)d.Ci * d.in_pitch * 4, (cuuint64_t)d.Ci * d.in_pitch * plane_rows * 4};
         cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)HALO_W, 3, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(d_x), dims, strides, box, estr,
@@ -866,7 +871,7 @@ int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w,
     } else {
         const long long planes = (long long)d.N * d.npart;
         cuuint64_t dims[4] = {(cuuint64_t)d.Ci, (cuuint64_t)d.in_pitch, (cuuint64_t)d.Hi, (cuuint64_t)planes};
-        cuuint64_t strides[3] = {(cuuint64_t)d.Ci * 4, (cuuint64_t)d.Ci * d.in_pitch * 4, (cuuint64_t)d.Ci * d.in_pitch * d.Hi * 4};
+        cuuint64_t strides[3] = {(cuuint64_t)d.Ci * 4, (cuuint64_t)d.Ci * d.in_pitch * 4, (cuuint64_t)d.Ci * d.in_pitch * plane_rows * 4};
         cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)(bw * d.stride), (cuuint32_t)(bh * d.stride), 1};
         cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
         CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(d_x), dims, strides, box, estr,

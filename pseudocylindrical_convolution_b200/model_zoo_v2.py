@@ -40,7 +40,7 @@ def pconv(x, conv: nn.Conv2d, npart, wl_out, prelu: nn.PReLU = None, sigmoid=Fal
     d.out_rows, d.out_pitch, d.out_y0, d.out_x0 = Ho, Wo, 0, 0
     d.k, d.stride = k, s
     d.act = ACT_PRELU if prelu is not None else (ACT_SIGMOID if sigmoid else ACT_NONE)
-    d.impl = config.CONV_IMPL if impl is None else impl
+    d.impl = 1 if impl is None else impl          # NCHW tensors: the fp32 direct form (the tensor-core path is transforms_nhwc)
     d.aux_rows, d.aux_pitch, d.aux_y0, d.aux_x0 = Ho, Wo, 0, 0
     for g in range(npart):
         d.wl_out[g] = min(int(wl_out[g]), Wo)
@@ -70,9 +70,18 @@ class _Block(nn.Module):
         super().__init__()
         self.npart = npart
         self._ctx = [ctx]          # shared geometry object, deliberately not registered as a submodule
+        self._nhwc = [None]
 
     def wl(self, x, h, W):
         return _widths(self._ctx[0], x, h, W)
+
+    def _runner(self):
+        """channels-last / tensor-core executor of this transform (transforms_nhwc.Runner), created on first use"""
+        if self._nhwc[0] is None:
+            from .transforms_nhwc import Runner
+            gid = next(self.parameters()).device.index
+            self._nhwc[0] = Runner(self._ctx[0].op[gid], self.npart)
+        return self._nhwc[0]
 
 
 class ResidualBlock(_Block):

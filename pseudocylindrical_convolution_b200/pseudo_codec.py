@@ -165,10 +165,23 @@ class PseudoEncoder(nn.Module):
     def symbols(self, x):
         """ERP image (1,3,H,W) -> symbol tensor (npart, valid_dim/4, H/128, W/8) fed to the entropy coder."""
         with torch.no_grad():
-            x = self.slice(x)
-            code = self.encoder(x)
-            _, code_i = self.quant(code)
-            return self.dtw(self.ext(code_i))
+            return self.dtw(self.ext(self.code(x)[1]))
+
+    def latent(self, x):
+        """ERP image -> analysis-transform output (npart, 192, H/256, W/16) in [0,1], before quantisation.  The transform
+        runs channels-last on the tcgen05 kernels (config.CONV_IMPL == 0, default) or as the NCHW fp32 exact-order path
+        (CONV_IMPL == 1)."""
+        from . import config
+        with torch.no_grad():
+            if config.CONV_IMPL == 1:
+                return self.encoder(self.slice(x))
+            from .transforms_nhwc import encoder_forward
+            return encoder_forward(self.encoder, x.contiguous(), self.slice.op[x.device.index])
+
+    def code(self, x):
+        """ERP image -> (dequantised code, symbols)"""
+        with torch.no_grad():
+            return self.quant(self.latent(x))
 
     def forward(self, x, code_name):
         with torch.no_grad():
@@ -199,8 +212,12 @@ class PseudoDecoder(nn.Module):
             n, _, h, w = code_ext.shape
             code_f = torch.zeros((n, self.code_channels, h, w)).type_as(code_ext)
             code_f[:, :self.valid_dim] = code_ext
-            tx = self.decoder(code_f.contiguous())
-            tx = self.uslice(tx)
+            from . import config
+            if config.CONV_IMPL == 1:
+                tx = self.uslice(self.decoder(code_f.contiguous()))
+            else:
+                from .transforms_nhwc import decoder_forward
+                tx = decoder_forward(self.decoder, code_f.contiguous(), self.uslice.op[code_f.device.index])
             return self.clip(tx)
 
     def forward(self, code_name, height=512, width=1024):

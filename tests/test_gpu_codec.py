@@ -1,0 +1,184 @@
+"""BASELINE configs[0]: pseudo_codec model-idx 3 (--ssim -> prefix '4_56', valid_dim 56) encode + decode of one synthetic
+512x1024 ERP image with seeded random-init weights, through the product's PseudoEncoder / PseudoDecoder (= the reference's
+classes, same state-dict keys, strict load).
+
+  * the decoder recovers the encoder's symbol tensor bit for bit from the bitstream (what decodability needs: both sides run
+    the same CUDA-core entropy path, whose arithmetic is pinned against the reference in test_golden_gpu.py);
+  * the tensor-core (TF32) transforms agree with the fp32 exact-order path and with a plain PyTorch fp32 evaluation of the
+    reference's layer sequence within the stated tolerances; symbol flips near bin edges are counted, not hidden."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import smooth_images
+
+pytestmark = pytest.mark.gpu
+H, W, VD, PREX = 512, 1024, 56, "4_56"
+
+
+@pytest.fixture(scope="module")
+def codec(cuda, tmp_path_factory):
+    import torch
+    from pseudocylindrical_convolution_b200 import pseudo_codec as pc
+    from pseudocylindrical_convolution_b200.random_init import synthesize_checkpoints
+    d = str(tmp_path_factory.mktemp("demo_ssim"))
+    p_enc, p_dec, p_ent = synthesize_checkpoints(d, PREX, VD, 0, seed=0)
+    enc = pc.PseudoEncoder(VD, 0).to(cuda)
+    dec = pc.PseudoDecoder(VD, 0).to(cuda)
+    pc.load_models(enc, p_enc, p_ent, "cuda:0")          # strict: the key sets are the reference's
+    pc.load_models(dec, p_dec, p_ent, "cuda:0")
+    x = torch.from_numpy(smooth_images(1, 3, H, W, seed=1234)).to(cuda)
+    return enc, dec, x, d
+
+
+def test_state_dict_contract(codec):
+    enc, dec, _, _ = codec
+    es, ds = enc.state_dict(), dec.state_dict()
+    assert len(es) == 186 and sum(v.numel() for v in es.values()) == 7237914
+    assert len(ds) == 191 and sum(v.numel() for v in ds.values()) == 11275302
+    assert tuple(es["ent.net.0.conv.weight"].shape) == (3, 42, 14, 5, 5)
+    assert tuple(ds["decoder.net.3.conv1.weight"].shape) == (768, 192, 3, 3)
+
+
+def test_encode_decode_roundtrip_is_lossless_on_symbols(codec, tmp_path):
+    import torch
+    enc, dec, x, _ = codec
+    sym = enc.symbols(x)
+    assert tuple(sym.shape) == (16, VD // 4, H // 128, W // 8)
+    s = sym.cpu().numpy()
+    assert set(np.unique(s)) <= set(range(8)) and len(np.unique(s)) >= 4
+    path = str(tmp_path / "img.bin")
+    enc(x, path)
+    nbytes = os.path.getsize(path)
+    bpp = nbytes * 8 / (H * W)
+    assert 0.01 < bpp < 3.0 * VD / 256 * 0.8164 + 0.1, bpp       # at most 3 bits per 8-level symbol
+    rec = dec(path, H, W)
+    assert tuple(rec.shape) == (1, 3, H, W) and torch.isfinite(rec).all()
+    # the decoder's entropy stage alone returns the symbol tensor
+    dec.ent.start(path)
+    got = dec.ent(H // 128, W // 8)
+    assert torch.equal(got, sym), "decoded symbols differ from the encoded ones"
+    # decoding twice gives the same bytes -> same reconstruction (deterministic kernels)
+    rec2 = dec(path, H, W)
+    assert torch.equal(rec, rec2)
+    print("bpp %.4f, %d bytes" % (bpp, nbytes))
+
+
+def _torch_reference_encoder(enc, x):
+    """The reference's layer sequence (model_zoo_v2.py:95-151) evaluated with plain PyTorch fp32 convolutions (TF32 off) and
+    this package's NCHW pad / fill operators (bit-exact to the reference's, test_golden_gpu.py)."""
+    import torch
+    import torch.nn.functional as F
+    e = enc.encoder
+
+    def fill(m, t):
+        return m.trim(t.contiguous())
+
+    def rb(m, t):
+        y = F.prelu(F.conv2d(m.pad(t), m.conv1.weight, m.conv1.bias), m.relu1.weight)      # no fill in between (reference :49-53)
+        y = F.prelu(F.conv2d(y, m.conv2.weight, m.conv2.bias), m.relu2.weight)
+        y = F.conv2d(y, m.conv3.weight, m.conv3.bias)
+        return fill(m, t + y)
+
+    def rbv2(m, t):
+        y = F.prelu(F.conv2d(m.pad(t), m.conv1.weight, m.conv1.bias), m.relu1.weight)
+        y = F.prelu(F.conv2d(y, m.conv2.weight, m.conv2.bias), m.relu2.weight)
+        return fill(m, t + y)
+
+    def gdn(m, t):
+        be, ge = m._effective()
+        NN, ch, h, Wd = t.shape
+        wl = m.ctx[0].op[0].widths(h, Wd)
+        mask = torch.zeros((NN, 1, 1, Wd), device=t.device)
+        for n in range(NN):
+            mask[n, 0, 0, :wl[n % 16]] = 1
+        t = t * mask
+        norm = torch.sqrt(F.conv2d(t * t, ge.view(ch, ch, 1, 1), be))
+        norm = norm * mask + 1 - mask
+        return t / norm
+
+    def down(m, t):
+        y = fill(m, F.prelu(F.conv2d(m.pad1(t), m.conv1.weight, m.conv1.bias, stride=2), m.relu1.weight))
+        y = gdn(m.relu2, fill(m, F.conv2d(m.pad2(y), m.conv2.weight, m.conv2.bias)))
+        s = F.conv2d(t, m.short_cut.weight, m.short_cut.bias, stride=2)
+        return fill(m, s + y)
+
+    def att(m, t):
+        a = t
+        tr = t
+        for i in range(3):
+            tr = rb(m.trunk[i], tr)
+            a = rb(m.attention[i], a)
+        a = torch.sigmoid(F.conv2d(a, m.attention[3].weight, m.attention[3].bias))
+        return fill(m, t + tr * a)
+
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            t = enc.slice(x)
+            t = down(e.net[0], t); t = rbv2(e.net[1], t); t = down(e.net[2], t); t = att(e.net[3], t)
+            t = rbv2(e.net[4], t); t = down(e.net[5], t); t = rbv2(e.net[6], t)
+            m = e.net[7]
+            t = fill(m, F.conv2d(m.pad(t), m.conv.weight, m.conv.bias, stride=2))
+            t = att(e.net[8], t)
+            return e.trim(torch.sigmoid(F.conv2d(t, e.net[9].weight, e.net[9].bias)).contiguous())
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_tensor_core_transforms_vs_fp32_paths(codec):
+    """Analysis transform: tcgen05 TF32 path vs (a) the NCHW fp32 exact-order kernels, (b) plain PyTorch fp32.
+    Tolerance on the sigmoid code (range [0,1], quantiser step ~0.12): max |diff| < 2e-2, rms < 2e-3; symbol flips < 2 %."""
+    import torch
+    from pseudocylindrical_convolution_b200 import config
+    enc, dec, x, _ = codec
+    lat_tc = enc.latent(x).clone()
+    sym_tc = enc.quant(lat_tc)[1].clone()
+    config.CONV_IMPL = 1
+    try:
+        lat_f = enc.latent(x).clone()
+    finally:
+        config.CONV_IMPL = 0
+    sym_f = enc.quant(lat_f)[1].clone()
+    ref = _torch_reference_encoder(enc, x)
+    q_ref = enc.quant(ref)[1].clone()
+    for name, a, b in (("tc vs fp32 direct", lat_tc, lat_f), ("fp32 direct vs torch fp32", lat_f, ref), ("tc vs torch fp32", lat_tc, ref)):
+        d = (a - b).abs()
+        print("%s: max %.3e rms %.3e" % (name, float(d.max()), float((d ** 2).mean().sqrt())))
+    d = (lat_f - ref).abs()
+    assert float(d.max()) < 2e-3, "the fp32 exact-order path must agree with PyTorch fp32 to rounding noise"
+    d = (lat_tc - ref).abs()
+    assert float(d.max()) < 2e-2 and float((d ** 2).mean().sqrt()) < 2e-3
+    flips = float((sym_tc != q_ref).float().mean())
+    print("symbol flips tc vs torch-fp32: %.4f %%, fp32-direct vs torch-fp32: %.4f %%" % (100 * flips, 100 * float((sym_f != q_ref).float().mean())))
+    assert flips < 0.02
+    assert float((sym_f != q_ref).float().mean()) < 0.002
+    code_tc = lat_tc
+    # invalid columns stay exactly zero on both paths
+    wl = enc.ctx.op[0].widths(code_tc.shape[2], code_tc.shape[3])
+    for g in range(16):
+        assert float(code_tc[g, :, :, wl[g]:].abs().max()) == 0.0 if wl[g] < code_tc.shape[3] else True
+
+
+def test_synthesis_transform_tc_vs_fp32(codec):
+    """Synthesis transform on the same symbols: reconstructions of the TF32 and fp32 exact-order paths agree to
+    max |diff| < 3e-2 (image range [0,1]) and PSNR between them > 50 dB."""
+    import math
+    import torch
+    from pseudocylindrical_convolution_b200 import config
+    enc, dec, x, _ = codec
+    sym = enc.symbols(x)
+    rec_tc = dec.reconstruct(sym).clone()
+    config.CONV_IMPL = 1
+    try:
+        rec_f = dec.reconstruct(sym).clone()
+    finally:
+        config.CONV_IMPL = 0
+    d = (rec_tc - rec_f).abs()
+    mse = float((d ** 2).mean())
+    print("recon tc vs fp32: max %.3e, PSNR between %.1f dB" % (float(d.max()), 10 * math.log10(1.0 / max(mse, 1e-20))))
+    assert torch.isfinite(rec_tc).all()
+    assert float(d.max()) < 3e-2 and mse < 1e-5
