@@ -35,6 +35,7 @@ extern "C" {
 
 #define PCX_MAX_PART 32
 #define PCX_MAX_GAUSS 16
+typedef struct pcx_coder pcx_coder;      /* host arithmetic coder handle, see the end of this header */
 
 enum {
     PCX_OK = 0,
@@ -215,6 +216,41 @@ int pcx_dextract_step(const float *d_in, float *d_out, int nrep, int npart, int 
 /* Fused wavefront step (B200-native): DInput2 + 12x(ctx pad + masked conv) + 5x add + DExtract2Batch +
  * GMM table for one step in ONE launch per layer group; same arithmetic as the separate entry points. */
 
+/* ---- wavefront engine (B200-native): the serial loops of EntEncoder.forward / EntDecoder.forward
+ * (pseudo_codec.py:97-114, :145-160) in one native call - same kernels, same CDFs, no per-operator host round trip; int32
+ * CDF rows of the live symbols only cross PCIe (pinned, asynchronous) and the host coder runs in the same loop, overlapped
+ * with the next step's kernels when encoding. */
+#define PCX_WAVE_MAX_LAYERS 16
+typedef struct pcx_wave_layer {
+    const float *weight;     /* (nb, G*go, G*gi, 5, 5)  EntropyConv2Batch.weight */
+    const float *bias;       /* (nb, G*go) */
+    const float *act;        /* (nb, G*go) PReLU slopes or NULL */
+    float *in;               /* (nb*nimg*npart, G*gi, h+2pad, W+2pad) padded input, halo refreshed in place */
+    float *out;              /* (nb*nimg*npart, G*go, h+2pad_out, W+2pad_out) */
+    const float *add;        /* EntropyAdd source added to `out` at the wavefront cells (same shape) or NULL */
+    int gi, go, pad_out, constrain, input_layer;
+} pcx_wave_layer;
+typedef struct pcx_wave_net {
+    int nlayers, nb, nimg, npart, G, h, W, pad, nstep, ng;
+    float gmm_bias, gmm_total, gmm_beta, input_bias;
+    const int *wl;                                   /* host, npart */
+    const int *d_band, *d_row, *d_col;               /* mode-1 halo table (pcx_halo_table) */
+    const float *d_tw;
+    const int *d_items;                              /* pcx_ctx_pad_items */
+    const int *h_pstart;
+    const int *d_order;                              /* pcx_ctx_order */
+    const int *h_start;
+    float *d_params;                                 /* (nb, go_last, h*npart, W) * nimg extraction buffer */
+    int *d_cdf;                                      /* (rows, nstep+1) int32 */
+    float *d_prev;                                   /* (nimg, h*npart*W) symbols of the previous step */
+    pcx_wave_layer layers[PCX_WAVE_MAX_LAYERS];
+} pcx_wave_net;
+int pcx_wave_steps(const pcx_wave_net *net);         /* h*npart + W + G - 2 */
+/* d_data (nimg*npart, G, h, W): symbols as float (PseudoFill'ed).  Encodes every symbol into `coder` (already started). */
+int pcx_wave_encode(const pcx_wave_net *net, const float *d_data, pcx_coder *coder, long long *n_symbols, void *stream);
+/* Decodes every symbol; on return layers[0].in holds symbol + input_bias at every valid cell (all nb replicas). */
+int pcx_wave_decode(const pcx_wave_net *net, pcx_coder *coder, long long *n_symbols, void *stream);
+
 /* ---- GMM ---------------------------------------------------------------------------------------------
  * EntropyGmmTableOp.forward_batch / forward (main.cpp:49-53 -> entropy_gmm_table_cuda.cu:107-185).
  * Softmax and delta clamp are applied IN PLACE on the inputs like the reference; d_cdf_f (n, nstep+1) fp32
@@ -230,7 +266,6 @@ int pcx_gmm_nll(const float *d_w, const float *d_delta, const float *d_mean, con
 /* ---- host arithmetic coder (coder/python.cpp:63-72 `coder.coder`) --------------------------------------
  * 32-bit-state range coder, MSB-first bit stream, no header, one terminating 1 bit then zero padding
  * (coder/ArithmeticCoder.cpp:34-69, :82-116, :152-154; coder/BitIoStream.cpp:52-72). */
-typedef struct pcx_coder pcx_coder;
 pcx_coder *pcx_coder_open(const char *path);          /* coder.coder(path)            */
 void pcx_coder_close(pcx_coder *c);
 int pcx_coder_start_encoder(pcx_coder *c);             /* start_encoder                */

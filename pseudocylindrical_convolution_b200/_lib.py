@@ -23,6 +23,21 @@ class ConvDesc(C.Structure):
         "k", "stride", "act", "impl", "aux_rows", "aux_pitch", "aux_y0", "aux_x0", "in_plane_rows")] + [("wl_out", C.c_int * PCX_MAX_PART)]
 
 
+class WaveLayer(C.Structure):
+    """struct pcx_wave_layer (include/pcx.h)."""
+    _fields_ = [("weight", C.c_void_p), ("bias", C.c_void_p), ("act", C.c_void_p), ("in_", C.c_void_p), ("out", C.c_void_p),
+                ("add", C.c_void_p)] + [(n, C.c_int) for n in ("gi", "go", "pad_out", "constrain", "input_layer")]
+
+
+class WaveNet(C.Structure):
+    """struct pcx_wave_net (include/pcx.h)."""
+    _fields_ = ([(n, C.c_int) for n in ("nlayers", "nb", "nimg", "npart", "G", "h", "W", "pad", "nstep", "ng")] +
+                [(n, C.c_float) for n in ("gmm_bias", "gmm_total", "gmm_beta", "input_bias")] +
+                [(n, C.c_void_p) for n in ("wl", "d_band", "d_row", "d_col", "d_tw", "d_items", "h_pstart", "d_order", "h_start",
+                                           "d_params", "d_cdf", "d_prev")] +
+                [("layers", WaveLayer * 16)])
+
+
 _P = C.c_void_p
 _I = C.c_int
 _F = C.c_float
@@ -65,6 +80,9 @@ PROTOTYPES = {
     "pcx_ctx_add_step": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _IP, _P]),
     "pcx_dinput_step": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _IP, _P]),
     "pcx_dextract_step": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _IP, _IP, _P]),
+    "pcx_wave_steps": (_I, [C.POINTER(WaveNet)]),
+    "pcx_wave_encode": (_I, [C.POINTER(WaveNet), _P, _P, C.POINTER(C.c_longlong), _P]),
+    "pcx_wave_decode": (_I, [C.POINTER(WaveNet), _P, C.POINTER(C.c_longlong), _P]),
     "pcx_gmm_table": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _I, _P, _P, _P]),
     "pcx_gmm_nll": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "pcx_coder_open": (_P, [C.c_char_p]),

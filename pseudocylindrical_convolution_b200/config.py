@@ -5,3 +5,8 @@ import os
 # kernels (TF32 operands, fp32 accumulate; transforms_nhwc.py), 1 = NCHW fp32 CUDA-core direct form (exact-order on-device
 # reference used by the parity tests; model_zoo_v2.pconv).
 CONV_IMPL = int(os.environ.get("PCX_CONV_IMPL", "0"))
+
+# wavefront (entropy) loop: 1 (default) = native engine (pcx_wave_encode / pcx_wave_decode: the whole serial loop in one
+# native call), 0 = operator-by-operator Python loop shaped like the reference's EntEncoder / EntDecoder.  Same kernels,
+# bit-identical CDF tables and bitstreams.
+WAVE_IMPL = int(os.environ.get("PCX_WAVE_IMPL", "1"))

@@ -407,3 +407,172 @@ int pcx_gmm_nll(const float *d_w, const float *d_delta, const float *d_mean, con
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ wavefront engine
+// The whole serial loop of EntEncoder / EntDecoder (pseudo_codec.py:97-114, :145-160) in native code: per step the same
+// launch sequence as the operator-by-operator path (DInput2 -> 12 x [EntropyCtxPadRun2 -> EntropyConv2Batch (+ EntropyAdd)]
+// -> DExtract2Batch -> EntropyBatchGmmTable), through the SAME kernels - so every CDF entry is bit-identical - but
+// without a Python / ctypes round trip per operator, with int32 CDF rows copied to pinned host memory (only the live
+// rows) and the host range coder called from the same loop.  The encoder is software-pipelined: the kernels of step
+// s+1 are enqueued before the host codes the tables of step s (labels come from the device-resident symbol tensor, so
+// there is no host dependency); the decoder has a true dependency per step (the symbols decoded at step s feed step s+1).
+namespace {
+
+struct PinnedPool {
+    int32_t *cdf[2] = {nullptr, nullptr};
+    float *lab[2] = {nullptr, nullptr};
+    float *d_prev = nullptr;
+    size_t rows = 0;
+};
+PinnedPool g_pin;
+
+int ensure_pinned(size_t rows, int nstep)
+{
+    if (rows <= g_pin.rows) return PCX_OK;
+    for (int i = 0; i < 2; i++) {
+        if (g_pin.cdf[i]) cudaFreeHost(g_pin.cdf[i]);
+        if (g_pin.lab[i]) cudaFreeHost(g_pin.lab[i]);
+        PCX_CUDA(cudaHostAlloc((void **)&g_pin.cdf[i], rows * (nstep + 1) * sizeof(int32_t), cudaHostAllocDefault));
+        PCX_CUDA(cudaHostAlloc((void **)&g_pin.lab[i], rows * sizeof(float), cudaHostAllocDefault));
+    }
+    g_pin.rows = rows;
+    return PCX_OK;
+}
+
+// one wavefront step on the device: returns the number of symbols (rows of the CDF table) it produced
+int wave_launch_step(const pcx_wave_net &n, int step, const float *d_prev, int *count, cudaStream_t s)
+{
+    const int nrep = n.nb * n.nimg;
+    int rc = pcx_dinput_step(d_prev, n.layers[0].in, n.nimg, n.npart, n.G, n.h, n.W, n.pad, n.input_bias, n.nb, step, n.d_order,
+                             n.h_start, s);
+    if (rc < 0) return rc;
+    for (int L = 0; L < n.nlayers; L++) {
+        const pcx_wave_layer &l = n.layers[L];
+        const i64 out_elems = (i64)nrep * n.npart * n.G * l.go * (n.h + 2 * l.pad_out) * (n.W + 2 * l.pad_out);
+        if (step == 0) PCX_CUDA(cudaMemsetAsync(l.out, 0, sizeof(float) * out_elems, s));       // entropy_conv_cuda_v2.cu:307-309
+        rc = pcx_ctx_pad_step(l.in, nrep, n.npart, n.G, l.gi, n.h, n.W, n.pad, l.input_layer ? step - 1 : step, n.wl, n.d_band,
+                              n.d_row, n.d_col, n.d_tw, n.d_items, n.h_pstart, s);
+        if (rc < 0) return rc;
+        rc = pcx_ctx_conv_step(l.in, l.weight, l.bias, l.act, l.out, n.nb, n.nimg, n.npart, n.G, l.gi, l.go, n.h, n.W, n.pad, l.pad_out,
+                               l.constrain, step, n.d_order, n.h_start, s);
+        if (rc < 0) return rc;
+        if (l.add) {
+            rc = pcx_ctx_add_step(l.out, l.add, nrep, n.npart, n.G, l.go, n.h, n.W, l.pad_out, step, n.d_order, n.h_start, s);
+            if (rc < 0) return rc;
+        }
+    }
+    const pcx_wave_layer &last = n.layers[n.nlayers - 1];
+    *count = 0;
+    rc = pcx_dextract_step(last.out, n.d_params, nrep, n.npart, n.G, last.go, n.h, n.W, step, 1, 0, n.d_order, n.h_start, count, s);
+    if (rc < 0) return rc;
+    const i64 stride = (i64)last.go * n.h * n.npart * n.W * n.nimg;
+    return pcx_gmm_table(n.d_params, n.d_params + stride, n.d_params + 2 * stride, *count, n.ng, n.nstep, n.gmm_bias, n.gmm_total,
+                         n.gmm_beta, 0, nullptr, n.d_cdf, s);
+}
+
+int wave_check(const pcx_wave_net *net)
+{
+    PCX_REQUIRE(net != nullptr, "null net");
+    const pcx_wave_net &n = *net;
+    PCX_REQUIRE(n.nlayers >= 1 && n.nlayers <= PCX_WAVE_MAX_LAYERS, "nlayers %d", n.nlayers);
+    PCX_REQUIRE(n.nb == 3 && n.nimg >= 1 && n.npart >= 1 && n.npart <= PCX_MAX_PART && n.G >= 1 && n.h >= 1 && n.W >= 1 && n.pad >= 1, "bad net shape");
+    PCX_REQUIRE(n.wl && n.d_band && n.d_row && n.d_col && n.d_tw && n.d_items && n.h_pstart && n.d_order && n.h_start && n.d_params && n.d_cdf && n.d_prev, "null table / buffer");
+    for (int L = 0; L < n.nlayers; L++)
+        PCX_REQUIRE(n.layers[L].weight && n.layers[L].bias && n.layers[L].in && n.layers[L].out, "layer %d has a null pointer", L);
+    PCX_REQUIRE(n.layers[n.nlayers - 1].pad_out == 0, "the last layer must have pad_out 0");
+    return PCX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pcx_wave_steps(const pcx_wave_net *net) { return net ? net->h * net->npart + net->W + net->G - 2 : PCX_EINVAL; }
+
+int pcx_wave_encode(const pcx_wave_net *net, const float *d_data, pcx_coder *coder, long long *n_symbols, void *stream)
+{
+    int rc = wave_check(net);
+    if (rc < 0) return rc;
+    PCX_REQUIRE(d_data && coder, "null data / coder");
+    const pcx_wave_net &n = *net;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int Hf = n.h * n.npart, nsteps = pcx_wave_steps(net);
+    const size_t max_rows = (size_t)n.nimg * (size_t)(Hf < n.W ? Hf : n.W) * n.G + 16;
+    rc = ensure_pinned(max_rows, n.nstep);
+    if (rc < 0) return rc;
+    cudaEvent_t ev[2];
+    for (auto &e : ev) PCX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    PCX_CUDA(cudaMemsetAsync(n.d_prev, 0, sizeof(float) * (size_t)n.nimg * Hf * n.W, s));      // label of "step -1" is all zero
+    int counts[2] = {0, 0};
+    long long total = 0;
+    int status = PCX_OK;
+    for (int step = 0; step <= nsteps && status == PCX_OK; step++) {
+        const int b = step & 1;
+        if (step < nsteps) {
+            int cnt = 0;
+            status = wave_launch_step(n, step, n.d_prev, &cnt, s);
+            if (status < 0) break;
+            // labels of this step = DExtract2(label=true) of the symbol tensor; they are next step's DInput2 source
+            int lcnt = 0;
+            status = pcx_dextract_step(d_data, n.d_prev, n.nimg, n.npart, n.G, 1, n.h, n.W, step, 0, 0, n.d_order, n.h_start, &lcnt, s);
+            if (status < 0) break;
+            counts[b] = cnt;
+            if (cnt > 0) {
+                PCX_CUDA(cudaMemcpyAsync(g_pin.cdf[b], n.d_cdf, sizeof(int32_t) * (size_t)cnt * (n.nstep + 1), cudaMemcpyDeviceToHost, s));
+                PCX_CUDA(cudaMemcpyAsync(g_pin.lab[b], n.d_prev, sizeof(float) * (size_t)cnt, cudaMemcpyDeviceToHost, s));
+            }
+            PCX_CUDA(cudaEventRecord(ev[b], s));
+        }
+        if (step > 0) {                             // code the previous step while the GPU runs this one
+            const int pb = (step - 1) & 1;
+            PCX_CUDA(cudaEventSynchronize(ev[pb]));
+            const int cnt = counts[pb];
+            if (cnt > 0) {
+                int32_t *lab = reinterpret_cast<int32_t *>(g_pin.lab[pb]);
+                for (int i = 0; i < cnt; i++) lab[i] = (int32_t)g_pin.lab[pb][i];            // symbols 0..7 stored as float
+                status = pcx_coder_encodes(coder, g_pin.cdf[pb], n.nstep, lab, cnt);
+                total += cnt;
+            }
+        }
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    if (n_symbols) *n_symbols = total;
+    return status;
+}
+
+int pcx_wave_decode(const pcx_wave_net *net, pcx_coder *coder, long long *n_symbols, void *stream)
+{
+    int rc = wave_check(net);
+    if (rc < 0) return rc;
+    PCX_REQUIRE(coder, "null coder");
+    const pcx_wave_net &n = *net;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int Hf = n.h * n.npart, nsteps = pcx_wave_steps(net);
+    const size_t max_rows = (size_t)n.nimg * (size_t)(Hf < n.W ? Hf : n.W) * n.G + 16;
+    rc = ensure_pinned(max_rows, n.nstep);
+    if (rc < 0) return rc;
+    PCX_CUDA(cudaMemsetAsync(n.d_prev, 0, sizeof(float) * (size_t)n.nimg * Hf * n.W, s));
+    long long total = 0;
+    for (int step = 0; step < nsteps; step++) {
+        int cnt = 0;
+        rc = wave_launch_step(n, step, n.d_prev, &cnt, s);
+        if (rc < 0) return rc;
+        if (cnt > 0) {
+            PCX_CUDA(cudaMemcpyAsync(g_pin.cdf[0], n.d_cdf, sizeof(int32_t) * (size_t)cnt * (n.nstep + 1), cudaMemcpyDeviceToHost, s));
+            PCX_CUDA(cudaStreamSynchronize(s));
+            rc = pcx_coder_decodes(coder, g_pin.cdf[0], n.nstep, cnt, g_pin.lab[0]);
+            if (rc < 0) return rc;
+            PCX_CUDA(cudaMemcpyAsync(n.d_prev, g_pin.lab[0], sizeof(float) * (size_t)cnt, cudaMemcpyHostToDevice, s));
+            total += cnt;
+        }
+    }
+    // the last step's symbols never pass through the network: one more DInput2 puts them into the padded input buffer,
+    // which then holds every decoded symbol (+ input_bias) - pseudo_codec.py:159
+    rc = pcx_dinput_step(n.d_prev, n.layers[0].in, n.nimg, n.npart, n.G, n.h, n.W, n.pad, n.input_bias, n.nb, nsteps, n.d_order, n.h_start, s);
+    if (rc < 0) return rc;
+    PCX_CUDA(cudaStreamSynchronize(s));
+    if (n_symbols) *n_symbols = total;
+    return PCX_OK;
+}
+
+}  // extern "C"

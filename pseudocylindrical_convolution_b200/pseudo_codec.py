@@ -88,6 +88,12 @@ class _EntBase(nn.Module):
         self.gmm = EntropyBatchGmmTable(bin_num, self.bias, 3, 65536, device=gid)
         self.net = self.net.to(self.cuda)
 
+    def engine(self):
+        if getattr(self, "_engine", None) is None:
+            from .wave_engine import WaveEngine
+            self._engine = WaveEngine(self)
+        return self._engine
+
     def start(self, code_name='./tmp/data'):
         self.apply(restart_entropy_network)
         self.mcoder = coder.coder(code_name)
@@ -109,11 +115,16 @@ class EntEncoder(_EntBase):
         self.ext_label = DExtract2(npart, ngroup, True, self.ctx2, device=gid)
 
     def forward(self, data):
+        from . import config
         with torch.no_grad():
             data = self.fill(data)
             h, w = data.shape[2:]
             self.ctx2.setup_context(w)
             self.mcoder.start_encoder()
+            if config.WAVE_IMPL == 1:           # native wavefront engine: same kernels and CDFs, one native call
+                self.engine().encode(data, self.mcoder)
+                self.mcoder.end_encoder()
+                return
             h_full = h * self.npart
             label = torch.zeros((1, 1, h_full, w), dtype=torch.float32).to(self.cuda)
             for _ in range(h_full + w + self.ngroup - 2):
@@ -130,9 +141,13 @@ class EntDecoder(_EntBase):
     """Inverse of EntEncoder: decodes (npart, ngroup, h, w) symbols from the bitstream (reference :117-160)."""
 
     def forward(self, h, w):
+        from . import config
         with torch.no_grad():
             self.ctx2.setup_context(w)
             self.mcoder.start_decoder()
+            if config.WAVE_IMPL == 1:
+                code = self.engine().decode(h, w, self.mcoder, torch.device(self.cuda))
+                return self.fill(code)
             h_full = h * self.npart
             pout = torch.zeros((1, 1, h_full, w), dtype=torch.float32).to(self.cuda)
             for _ in range(h_full + w + self.ngroup - 2):
