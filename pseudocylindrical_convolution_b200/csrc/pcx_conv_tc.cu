@@ -28,8 +28,8 @@ constexpr int BLOCK_K = 32;           // input channels per pipeline stage (= on
 constexpr int UMMA_K = 8;             // tf32
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;     // 16 KB: 128 pixel rows x 128 B
 constexpr int NUM_THREADS = 192;      // 6 warps
-constexpr int MAX_CO_STAGED = 1024;   // bias + PReLU slope vectors staged in shared memory (2 x 4 KB)
-constexpr int VEC_SMEM = 2 * MAX_CO_STAGED * 4;
+constexpr int MAX_CO_STAGED = 768;    // bias + PReLU slope vectors staged in shared memory (2 x 3 KB)
+constexpr int VEC_SMEM = 2 * MAX_CO_STAGED * 4 + 4 * 32 * 36 * 4;   // + the epilogue warps' transpose tiles
 
 struct TcParams {
     int planes, npart;
@@ -178,73 +178,103 @@ __device__ __forceinline__ bool tile_live(const TcParams &p, const Tile &t)
 }
 
 
-// One output pixel (= one TMEM lane) of a finished accumulator tile: TMEM -> registers -> bias, PReLU / sigmoid, gate,
-// residual, invalid-column zeroing -> 128-bit NHWC stores.  `taddr` = TMEM address of this warp's lane quadrant and of
-// the accumulator stage's first column.  `bias` / `slope` point to the per-channel vectors staged in SHARED memory
-// (broadcast LDS; the global copies would be re-fetched from L2 after every cluster-scope acquire, which
-// invalidates L1 - that made the first pair kernel epilogue-bound).
-template <int NT>
-__device__ __forceinline__ void epilogue_pixel(const TcParams &p, long long plane, int oy, int ox, int n0, bool live, bool in_plane,
-                                               bool valid, uint32_t taddr0, const float *__restrict__ bias,
-                                               const float *__restrict__ slope, const float *__restrict__ mul,
-                                               const float *__restrict__ residual, float *__restrict__ y)
+// Epilogue of one warp = 32 consecutive pixels of one tile row (TMEM lanes) x NT channels of a finished accumulator.
+// TMEM hands every LANE one pixel with 32 channels in registers; written like that, a warp-level 128-bit access touches 32
+// different 768-byte-strided lines (the first version: the GDN / residual 1x1 layers ran at a quarter of the HBM rate).
+// Here each 32-pixel x 32-channel chunk is transposed through a per-warp shared-memory tile (pitch 36 floats, conflict
+// free both ways) so that 8 lanes cover the 128 contiguous bytes of one pixel: every global load (gate, residual) and
+// store is four full 128-byte lines.  Math order per element is unchanged: +bias, act, *mul, +residual, fill.
+// `bias` / `slope` point to the per-channel vectors staged in SHARED memory (broadcast LDS; the global copies would be
+// re-fetched from L2 after every cluster-scope acquire, which invalidates L1).
+constexpr int EPI_PITCH = 36;
+constexpr int EPI_SMEM = 4 * 32 * EPI_PITCH * 4;       // four epilogue warps
+
+template <int NT, int ACTK, bool DBG = false>
+__device__ __forceinline__ void epilogue_warp(const TcParams &p, long long plane, int oy, int ox0, int n0, bool live, int wl, uint32_t taddr0,
+                                              float *__restrict__ stage, const float *__restrict__ bias, const float *__restrict__ slope,
+                                              const float *__restrict__ mul, const float *__restrict__ residual, float *__restrict__ y,
+                                              long long *t_ld = nullptr)
 {
+    const int lane = threadIdx.x & 31;
     const int nco = min(NT, p.Co - n0 * NT);       // multiple of 4
     const int cbase = n0 * NT;
-    float *yp = y + (((plane * p.out_rows + oy + p.out_y0) * (long long)p.out_pitch) + ox + p.out_x0) * p.Co + cbase;
-    const long long aoff = (((plane * p.aux_rows + oy + p.aux_y0) * (long long)p.aux_pitch) + ox + p.aux_x0) * p.Co + cbase;
+    const bool row_ok = oy < p.Ho;
+    // lane -> (pixel sub-index, 16-byte channel chunk) of the transposed view
+    const int psub = lane >> 3, cch = lane & 7;
+    float *yrow = y + (((plane * p.out_rows + oy + p.out_y0) * (long long)p.out_pitch) + ox0 + p.out_x0) * p.Co + cbase + cch * 4;
+    const long long arow = (((plane * p.aux_rows + oy + p.aux_y0) * (long long)p.aux_pitch) + ox0 + p.aux_x0) * p.Co + cbase + cch * 4;
     constexpr int STEP = NT >= 32 ? 32 : 16;
+    constexpr int CCH = STEP / 4;                  // 16-byte chunks per pixel and step (8 or 4)
 #pragma unroll 1
     for (int c0 = 0; c0 < NT; c0 += STEP) {
-        uint32_t v[STEP];
         if (live) {
+            uint32_t v[STEP];
             const uint32_t taddr = taddr0 + (uint32_t)c0;
+            long long t0 = 0;
+            if (DBG) t0 = clock64();
             if constexpr (STEP == 32) tmem_ld32(taddr, v);
             else tmem_ld16(taddr, v);
             tmem_wait_ld();
-        }
-        if (in_plane) {
+            if (DBG) *t_ld += clock64() - t0;
+            float *sw = stage + lane * EPI_PITCH;
 #pragma unroll
-            for (int j = 0; j < STEP; j += 4) {
-                const int co = c0 + j;
-                if (co >= nco) break;
-                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) {
-                    r = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                    if (bias) {
-                        const float4 b4 = *reinterpret_cast<const float4 *>(bias + cbase + co);
-                        r.x = __fadd_rn(r.x, b4.x); r.y = __fadd_rn(r.y, b4.y); r.z = __fadd_rn(r.z, b4.z); r.w = __fadd_rn(r.w, b4.w);
-                    }
-                    if (p.act == 1) {
-                        const float4 s4 = *reinterpret_cast<const float4 *>(slope + cbase + co);
-                        if (r.x < 0.f) r.x = __fmul_rn(r.x, s4.x);
-                        if (r.y < 0.f) r.y = __fmul_rn(r.y, s4.y);
-                        if (r.z < 0.f) r.z = __fmul_rn(r.z, s4.z);
-                        if (r.w < 0.f) r.w = __fmul_rn(r.w, s4.w);
-                    } else if (p.act == 2) {
-                        r.x = 1.0f / (1.0f + expf(-r.x)); r.y = 1.0f / (1.0f + expf(-r.y));
-                        r.z = 1.0f / (1.0f + expf(-r.z)); r.w = 1.0f / (1.0f + expf(-r.w));
-                    } else if (p.act == 3) {
-                        r.x = 1.0f / sqrtf(r.x); r.y = 1.0f / sqrtf(r.y); r.z = 1.0f / sqrtf(r.z); r.w = 1.0f / sqrtf(r.w);
-                    } else if (p.act == 4) {
-                        r.x = sqrtf(r.x); r.y = sqrtf(r.y); r.z = sqrtf(r.z); r.w = sqrtf(r.w);
-                    }
-                    if (mul) {
-                        const float4 m4 = __ldg(reinterpret_cast<const float4 *>(mul + aoff + co));
-                        r.x = __fmul_rn(r.x, m4.x); r.y = __fmul_rn(r.y, m4.y); r.z = __fmul_rn(r.z, m4.z); r.w = __fmul_rn(r.w, m4.w);
-                    }
-                    if (residual) {
-                        const float4 a4 = __ldg(reinterpret_cast<const float4 *>(residual + aoff + co));
-                        r.x = __fadd_rn(a4.x, r.x); r.y = __fadd_rn(a4.y, r.y); r.z = __fadd_rn(a4.z, r.z); r.w = __fadd_rn(a4.w, r.w);
-                    }
+            for (int j = 0; j < STEP; j += 4)
+                *reinterpret_cast<float4 *>(sw + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        }
+        __syncwarp();
+        const int co = c0 + cch * 4;
+        if (row_ok && cch < CCH && co < nco) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = b4;
+            if (bias) b4 = *reinterpret_cast<const float4 *>(bias + cbase + co);
+            if (p.act == 1) s4 = *reinterpret_cast<const float4 *>(slope + cbase + co);
+            // gate / residual operands of all eight pixels of this lane first: sixteen independent 128-bit loads in flight
+            // (issued one by one inside the loop they serialised two L2 round trips per pixel - the GDN / residual layers
+            // got slower, not faster, with the coalesced layout; profiles/r1k_*)
+            float4 m4[8], a4[8];
+            if (mul || residual) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int px = i * 4 + psub;
+                    const bool ok = live && ox0 + px < wl && ox0 + px < p.Wo;
+                    const long long ao = arow + (long long)px * p.Co + c0;
+                    m4[i] = (mul && ok) ? __ldg(reinterpret_cast<const float4 *>(mul + ao)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    a4[i] = (residual && ok) ? __ldg(reinterpret_cast<const float4 *>(residual + ao)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                *reinterpret_cast<float4 *>(yp + co) = r;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int px = i * 4 + psub;
+                const int ox = ox0 + px;
+                if (ox < p.Wo) {
+                    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (live && ox < wl) {
+                        r = *reinterpret_cast<const float4 *>(stage + px * EPI_PITCH + cch * 4);
+                        if (bias) { r.x = __fadd_rn(r.x, b4.x); r.y = __fadd_rn(r.y, b4.y); r.z = __fadd_rn(r.z, b4.z); r.w = __fadd_rn(r.w, b4.w); }
+                        if (p.act == 1) {
+                            if (r.x < 0.f) r.x = __fmul_rn(r.x, s4.x);
+                            if (r.y < 0.f) r.y = __fmul_rn(r.y, s4.y);
+                            if (r.z < 0.f) r.z = __fmul_rn(r.z, s4.z);
+                            if (r.w < 0.f) r.w = __fmul_rn(r.w, s4.w);
+                        } else if (ACTK == 2) {     // sigmoid / rsqrt / sqrt live in separate kernel instances (ACTK = the act code):
+                            r.x = 1.0f / (1.0f + expf(-r.x)); r.y = 1.0f / (1.0f + expf(-r.y));      // inlined together they pushed the
+                            r.z = 1.0f / (1.0f + expf(-r.z)); r.w = 1.0f / (1.0f + expf(-r.w));      // kernels out of the instruction cache
+                        } else if (ACTK == 3) {
+                            r.x = 1.0f / sqrtf(r.x); r.y = 1.0f / sqrtf(r.y); r.z = 1.0f / sqrtf(r.z); r.w = 1.0f / sqrtf(r.w);
+                        } else if (ACTK == 4) {
+                            r.x = sqrtf(r.x); r.y = sqrtf(r.y); r.z = sqrtf(r.z); r.w = sqrtf(r.w);
+                        }
+                        if (mul) { r.x = __fmul_rn(r.x, m4[i].x); r.y = __fmul_rn(r.y, m4[i].y); r.z = __fmul_rn(r.z, m4[i].z); r.w = __fmul_rn(r.w, m4[i].w); }
+                        if (residual) { r.x = __fadd_rn(a4[i].x, r.x); r.y = __fadd_rn(a4[i].y, r.y); r.z = __fadd_rn(a4[i].z, r.z); r.w = __fadd_rn(a4[i].w, r.w); }
+                    }
+                    *reinterpret_cast<float4 *>(yrow + (long long)px * p.Co + c0) = r;
+                }
             }
         }
+        __syncwarp();
     }
 }
 
-template <int NT>
+template <int NT, int ACTK>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                   const __grid_constant__ CUtensorMap map_w, TcParams p,
                                                                   const float *__restrict__ bias, const float *__restrict__ slope,
@@ -263,6 +293,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
     float *s_bias = reinterpret_cast<float *>(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256);
     float *s_slope = s_bias + MAX_CO_STAGED;
+    float *s_stage = s_slope + MAX_CO_STAGED;
     stage_channel_vectors(s_bias, s_slope, bias, slope, p.Co);
 
     const int warp = threadIdx.x >> 5;
@@ -362,17 +393,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             Tile tl = decode_tile(p, t);
             const int g = (int)(tl.plane % p.npart);
             const int wl = p.wl_out[g];
-            const int oy = tl.y0 + m / p.bw;
-            const int ox = tl.x0 + m % p.bw;
-            const bool in_plane = oy < p.Ho && ox < p.Wo;
-            const bool valid = in_plane && ox < wl;
+            const int m0 = q * 32;                       // first pixel of this warp: 32 consecutive pixels of one tile row (32 | bw)
+            const int oy = tl.y0 + m0 / p.bw;
+            const int ox0 = tl.x0 + m0 % p.bw;
             const bool live = tile_live(p, tl);
             if (live) {
                 mbar_wait(&acc_full[acc], acc_phase);
                 tc_fence_after();
             }
-            epilogue_pixel<NT>(p, tl.plane, oy, ox, tl.n0, live, in_plane, valid, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT),
-                               bias ? s_bias : nullptr, s_slope, mul, residual, y);
+            epilogue_warp<NT, ACTK>(p, tl.plane, oy, ox0, tl.n0, live, wl, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT),
+                                     s_stage + q * 32 * EPI_PITCH, bias ? s_bias : nullptr, s_slope, mul, residual, y);
             if (live) {
                 tc_fence_before();
                 __syncwarp();
@@ -524,7 +554,7 @@ __device__ __forceinline__ PairTile decode_pair(const TcParams &p, long long t)
     return r;
 }
 
-template <int NT, bool DBG>
+template <int NT, int ACTK, bool DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     conv_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, TcParams p,
                      const float *__restrict__ bias, const float *__restrict__ slope, const float *__restrict__ mul,
@@ -544,6 +574,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
     float *s_bias = reinterpret_cast<float *>(b_base + (size_t)B2_STAGES * C::B_STAGE + 512);
     float *s_slope = s_bias + MAX_CO_STAGED;
+    float *s_stage = s_slope + MAX_CO_STAGED;
     stage_channel_vectors(s_bias, s_slope, bias, slope, p.Co);
 
     const int warp = threadIdx.x >> 5;
@@ -657,29 +688,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     } else {
         // ===================================================================================== epilogue warps (both CTAs)
         const int q = warp & 3;
-        const int m = q * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
+        long long ep_wait = 0, ep_work = 0, ep_ld = 0;
         for (long long t = cluster_id; t < p.total_tiles; t += n_clusters) {
             PairTile tl = decode_pair(p, t);
             const int wl = p.wl_out[(int)(tl.plane % p.npart)];
             const int oy = tl.y0 + (int)rank;
-            const int ox = tl.x0 + m;
-            const bool in_plane = oy < p.Ho && ox < p.Wo;
-            const bool valid = in_plane && ox < wl;
+            const int ox0 = tl.x0 + q * 32;
             const bool live = tl.x0 < wl;
+            long long e0 = 0, e1 = 0;
+            if (DBG) e0 = clock64();
             if (live) {
                 mbar_wait(&acc_full[acc], acc_phase);
                 tc_fence_after();
             }
-            epilogue_pixel<NT>(p, tl.plane, oy, ox, tl.n0, live, in_plane, valid, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT),
-                               bias ? s_bias : nullptr, s_slope, mul, residual, y);
+            if (DBG) e1 = clock64();
+            epilogue_warp<NT, ACTK, DBG>(p, tl.plane, oy, ox0, tl.n0, live, wl, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT),
+                                   s_stage + q * 32 * EPI_PITCH, bias ? s_bias : nullptr, s_slope, mul, residual, y, &ep_ld);
+            if (DBG) { ep_wait += e1 - e0; ep_work += clock64() - e1; }
             if (live) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(leader_addr(&acc_empty[acc]));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+        }
+        if (DBG && p.dbg && warp == 2 && lane == 0 && rank == 0) {
+            long long *d = p.dbg + 4 * 74 + 2 * cluster_id;
+            d[0] = ep_wait; d[1] = ep_work; p.dbg[6 * 74 + cluster_id] = ep_ld;
         }
     }
     tc_fence_before();
@@ -760,44 +797,64 @@ extern "C" long long pcx_conv_pack_weights(const float *d_w, float *d_out, int C
     return total;
 }
 
-template <int NT>
-static int launch_tc(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, const float *bias, const float *slope,
+template <int NT, int ACTK>
+static int launch_tc_v(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, const float *bias, const float *slope,
                      const float *mul, const float *residual, float *y, cudaStream_t s)
 {
     using C = Cfg<NT>;
     static bool attr = false;
     if (!attr) {
-        PCX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        PCX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT, ACTK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         attr = true;
     }
     long long grid = p.total_tiles < pcx_sm_count() ? p.total_tiles : pcx_sm_count();
-    conv_tc_kernel<NT><<<(unsigned)grid, NUM_THREADS, C::SMEM, s>>>(mx, mw, p, bias, slope, mul, residual, y);
+    conv_tc_kernel<NT, ACTK><<<(unsigned)grid, NUM_THREADS, C::SMEM, s>>>(mx, mw, p, bias, slope, mul, residual, y);
     PCX_LAUNCHED();
     return PCX_OK;
 }
 
 
-template <int NT, bool DBG = false>
-static int launch_pair(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, const float *bias, const float *slope,
+template <int NT, int ACTK, bool DBG>
+static int launch_pair_v(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, const float *bias, const float *slope,
                        const float *mul, const float *residual, float *y, cudaStream_t s)
 {
     using C = Cfg2<NT>;
     static int max_clusters = 0;
     if (max_clusters == 0) {
-        PCX_CUDA(cudaFuncSetAttribute(conv_pair_kernel<NT, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        PCX_CUDA(cudaFuncSetAttribute(conv_pair_kernel<NT, ACTK, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(pcx_sm_count() / 2 * 2);
         cfg.blockDim = dim3(NUM_THREADS);
         cfg.dynamicSmemBytes = C::SMEM;
         int n = 0;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, conv_pair_kernel<NT, DBG>, &cfg);
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, conv_pair_kernel<NT, ACTK, DBG>, &cfg);
         if (e != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = pcx_sm_count() / 2; }
         max_clusters = n;
     }
     long long clusters = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;
-    conv_pair_kernel<NT, DBG><<<(unsigned)(2 * clusters), NUM_THREADS, C::SMEM, s>>>(mx, mw, p, bias, slope, mul, residual, y);
+    conv_pair_kernel<NT, ACTK, DBG><<<(unsigned)(2 * clusters), NUM_THREADS, C::SMEM, s>>>(mx, mw, p, bias, slope, mul, residual, y);
     PCX_LAUNCHED();
     return PCX_OK;
+}
+
+
+template <int NT>
+static int launch_tc(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, const float *bias, const float *slope,
+                     const float *mul, const float *residual, float *y, cudaStream_t s)
+{
+    switch (p.act) {
+    case 2: return launch_tc_v<NT, 2>(mx, mw, p, bias, slope, mul, residual, y, s);
+    case 3: return launch_tc_v<NT, 3>(mx, mw, p, bias, slope, mul, residual, y, s);
+    case 4: return launch_tc_v<NT, 4>(mx, mw, p, bias, slope, mul, residual, y, s);
+    default: return launch_tc_v<NT, 0>(mx, mw, p, bias, slope, mul, residual, y, s);
+    }
+}
+template <int NT, bool DBG = false>
+static int launch_pair(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, const float *bias, const float *slope,
+                       const float *mul, const float *residual, float *y, cudaStream_t s)
+{
+    // transcendental epilogues only occur on 1x1 layers (sigmoid gates, GDN) - the pair kernel is 3x3 only
+    return launch_pair_v<NT, 0, DBG>(mx, mw, p, bias, slope, mul, residual, y, s);
 }
 
 static int pair_mode()
@@ -852,7 +909,7 @@ int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w,
         if (rc < 0) return (int)rc;
     }
 
-    const bool pair = pair_mode() != 0 && d.k == 3 && d.stride == 1 && d.Wo >= 64;
+    const bool pair = pair_mode() != 0 && d.k == 3 && d.stride == 1 && d.Wo >= 64 && d.act <= 1;
     const cuuint64_t plane_rows = (cuuint64_t)(d.in_plane_rows > 0 ? d.in_plane_rows : d.Hi);
 
     // ---- tensor maps
@@ -907,7 +964,7 @@ int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w,
     if (pair) {
         static long long *dbg = nullptr;
         if (getenv("PCX_TC_DEBUG")) {
-            if (!dbg) { cudaMalloc(&dbg, 4 * 128 * sizeof(long long)); }
+            if (!dbg) { cudaMalloc(&dbg, 8 * 128 * sizeof(long long)); }
             p.dbg = dbg;
         }
         p.bw = BLOCK_M; p.bh = 1;
@@ -920,12 +977,12 @@ int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w,
                                            : launch_pair<16, true>(mx, mw, p, d_bias, d_slope, d_mul, d_residual, d_y, s));
             static int printed = 0;
             if (printed++ < 3) {
-                long long h[4 * 74];
+                long long h[7 * 74];
                 cudaStreamSynchronize(s);
                 cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
                 for (int c = 0; c < 74; c += 18)
-                    fprintf(stderr, "[pcx dbg] cluster %2d: total %lld clk, wait acc_empty %lld, a_full %lld, b_full %lld\n", c, h[4 * c], h[4 * c + 1],
-                            h[4 * c + 2], h[4 * c + 3]);
+                    fprintf(stderr, "[pcx dbg] cluster %2d: total %lld clk, wait acc_empty %lld, a_full %lld, b_full %lld | epilogue warp: wait acc_full %lld, work %lld of which tcgen05.ld %lld\n",
+                            c, h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3], h[4 * 74 + 2 * c], h[4 * 74 + 2 * c + 1], h[6 * 74 + c]);
             }
             return rc;
         }
