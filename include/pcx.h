@@ -246,10 +246,12 @@ typedef struct pcx_wave_net {
     pcx_wave_layer layers[PCX_WAVE_MAX_LAYERS];
 } pcx_wave_net;
 int pcx_wave_steps(const pcx_wave_net *net);         /* h*npart + W + G - 2 */
-/* d_data (nimg*npart, G, h, W): symbols as float (PseudoFill'ed).  Encodes every symbol into `coder` (already started). */
-int pcx_wave_encode(const pcx_wave_net *net, const float *d_data, pcx_coder *coder, long long *n_symbols, void *stream);
-/* Decodes every symbol; on return layers[0].in holds symbol + input_bias at every valid cell (all nb replicas). */
-int pcx_wave_decode(const pcx_wave_net *net, pcx_coder *coder, long long *n_symbols, void *stream);
+/* d_data (nimg*npart, G, h, W): symbols as float (PseudoFill'ed).  Image i is coded into coders[i] (already started): the
+ * nimg images advance through the wavefront together - same step count, nimg times the work per launch - and each
+ * gets its own headerless bitstream, identical to coding it alone. */
+int pcx_wave_encode(const pcx_wave_net *net, const float *d_data, pcx_coder *const *coders, long long *n_symbols, void *stream);
+/* Decodes every symbol of the nimg bitstreams; on return layers[0].in holds symbol + input_bias at every valid cell. */
+int pcx_wave_decode(const pcx_wave_net *net, pcx_coder *const *coders, long long *n_symbols, void *stream);
 
 /* ---- GMM ---------------------------------------------------------------------------------------------
  * EntropyGmmTableOp.forward_batch / forward (main.cpp:49-53 -> entropy_gmm_table_cuda.cu:107-185).

@@ -7,6 +7,10 @@
 // scalar: lane l carries virtual lanes l, l+32, l+64 in registers, so the folds are register adds and the
 // tail is the same shuffle tree - bit-identical results with a quarter of the threads and no shared memory.
 #include "pcx_common.cuh"
+#include <stdlib.h>
+#include <atomic>
+#include <thread>
+#include <vector>
 
 namespace {
 
@@ -121,6 +125,7 @@ __global__ void __launch_bounds__(256) ctx_conv_kernel(const float *__restrict__
         out[((qn * Co + pout) * oh + th + pad_out) * ow + tw + pad_out] = sum;
     }
 }
+
 
 // entropy_add_forward_kernel (extension/entropy_add_cuda.cu:25-44)
 __global__ void ctx_add_kernel(float *__restrict__ y, const float *__restrict__ x, const int *__restrict__ order, int first,
@@ -302,9 +307,9 @@ int pcx_ctx_conv_step(const float *d_in, const float *d_weight, const float *d_b
     if (w.count <= 0) return PCX_OK;
     i64 nscalars = (i64)nb * nimg * go * w.count;
     PCX_REQUIRE(nscalars < (1ll << 26), "wavefront too large");
+    cudaStream_t s = (cudaStream_t)stream;
     const int threads = 256;
     int blocks = grid_for(nscalars * 32, threads);
-    cudaStream_t s = (cudaStream_t)stream;
     if (gi == 1)
         ctx_conv_kernel<1><<<blocks, threads, 0, s>>>(d_in, d_weight, d_bias, d_act, d_out, d_order, w.first, w.count, nimg,
                                                       (int)nscalars, npart, G, go, h, W, pad_in, pad_out, constrain, psum);
@@ -426,6 +431,64 @@ struct PinnedPool {
 };
 PinnedPool g_pin;
 
+
+// Per-image host coding in parallel: the nimg bitstreams are independent, so every wavefront step hands image i's rows to
+// worker i (the calling thread takes image 0).  Workers spin on a generation counter - a step's coding job is tens of
+// microseconds, far below a condition variable's wake-up latency - and live only for the duration of one encode / decode.
+struct CoderPool {
+    pcx_coder *const *coders = nullptr;
+    int nimg = 1, ncode = 8;
+    bool encode = true;
+    // job of the current generation
+    const int32_t *cdf = nullptr;
+    int32_t *lab_i = nullptr;     // encode: symbols in
+    float *lab_f = nullptr;       // decode: symbols out
+    int per = 0;
+    std::atomic<int> gen{0}, done{0}, status{0};
+    std::atomic<bool> quit{false};
+    std::vector<std::thread> threads;
+
+    void work(int im)
+    {
+        int rc;
+        if (encode) rc = pcx_coder_encodes(coders[im], cdf + (size_t)im * per * (ncode + 1), ncode, lab_i + (size_t)im * per, per);
+        else rc = pcx_coder_decodes(coders[im], cdf + (size_t)im * per * (ncode + 1), ncode, per, lab_f + (size_t)im * per);
+        if (rc < 0) status.store(rc);
+    }
+    void loop(int im)
+    {
+        int seen = 0;
+        for (;;) {
+            int spins = 0;
+            while (gen.load(std::memory_order_acquire) == seen && !quit.load(std::memory_order_relaxed))
+                if (++spins > 2000) std::this_thread::yield();
+            if (quit.load()) return;
+            seen = gen.load(std::memory_order_acquire);
+            work(im);
+            done.fetch_add(1, std::memory_order_release);
+        }
+    }
+    void start(pcx_coder *const *c, int n, int nc, bool enc)
+    {
+        coders = c; nimg = n; ncode = nc; encode = enc;
+        for (int im = 1; im < nimg; im++) threads.emplace_back([this, im] { loop(im); });
+    }
+    int run(const int32_t *cdf_, int32_t *li, float *lf, int per_)
+    {
+        cdf = cdf_; lab_i = li; lab_f = lf; per = per_;
+        done.store(0, std::memory_order_relaxed);
+        gen.fetch_add(1, std::memory_order_release);
+        work(0);
+        while (done.load(std::memory_order_acquire) < nimg - 1) { }
+        return status.load();
+    }
+    ~CoderPool()
+    {
+        quit.store(true);
+        for (auto &t : threads) t.join();
+    }
+};
+
 int ensure_pinned(size_t rows, int nstep)
 {
     if (rows <= g_pin.rows) return PCX_OK;
@@ -489,11 +552,12 @@ extern "C" {
 
 int pcx_wave_steps(const pcx_wave_net *net) { return net ? net->h * net->npart + net->W + net->G - 2 : PCX_EINVAL; }
 
-int pcx_wave_encode(const pcx_wave_net *net, const float *d_data, pcx_coder *coder, long long *n_symbols, void *stream)
+int pcx_wave_encode(const pcx_wave_net *net, const float *d_data, pcx_coder *const *coders, long long *n_symbols, void *stream)
 {
     int rc = wave_check(net);
     if (rc < 0) return rc;
-    PCX_REQUIRE(d_data && coder, "null data / coder");
+    PCX_REQUIRE(d_data && coders, "null data / coders");
+    for (int i = 0; i < net->nimg; i++) PCX_REQUIRE(coders[i] != nullptr, "null coder for image %d", i);
     const pcx_wave_net &n = *net;
     cudaStream_t s = (cudaStream_t)stream;
     const int Hf = n.h * n.npart, nsteps = pcx_wave_steps(net);
@@ -506,6 +570,8 @@ int pcx_wave_encode(const pcx_wave_net *net, const float *d_data, pcx_coder *cod
     int counts[2] = {0, 0};
     long long total = 0;
     int status = PCX_OK;
+    CoderPool pool;
+    pool.start(coders, n.nimg, n.nstep, true);
     for (int step = 0; step <= nsteps && status == PCX_OK; step++) {
         const int b = step & 1;
         if (step < nsteps) {
@@ -530,7 +596,8 @@ int pcx_wave_encode(const pcx_wave_net *net, const float *d_data, pcx_coder *cod
             if (cnt > 0) {
                 int32_t *lab = reinterpret_cast<int32_t *>(g_pin.lab[pb]);
                 for (int i = 0; i < cnt; i++) lab[i] = (int32_t)g_pin.lab[pb][i];            // symbols 0..7 stored as float
-                status = pcx_coder_encodes(coder, g_pin.cdf[pb], n.nstep, lab, cnt);
+                // rows are ordered (image, cell of the window): every image has its own bitstream and its own host thread
+                status = pool.run(g_pin.cdf[pb], lab, nullptr, cnt / n.nimg);
                 total += cnt;
             }
         }
@@ -540,11 +607,12 @@ int pcx_wave_encode(const pcx_wave_net *net, const float *d_data, pcx_coder *cod
     return status;
 }
 
-int pcx_wave_decode(const pcx_wave_net *net, pcx_coder *coder, long long *n_symbols, void *stream)
+int pcx_wave_decode(const pcx_wave_net *net, pcx_coder *const *coders, long long *n_symbols, void *stream)
 {
     int rc = wave_check(net);
     if (rc < 0) return rc;
-    PCX_REQUIRE(coder, "null coder");
+    PCX_REQUIRE(coders, "null coders");
+    for (int i = 0; i < net->nimg; i++) PCX_REQUIRE(coders[i] != nullptr, "null coder for image %d", i);
     const pcx_wave_net &n = *net;
     cudaStream_t s = (cudaStream_t)stream;
     const int Hf = n.h * n.npart, nsteps = pcx_wave_steps(net);
@@ -553,6 +621,8 @@ int pcx_wave_decode(const pcx_wave_net *net, pcx_coder *coder, long long *n_symb
     if (rc < 0) return rc;
     PCX_CUDA(cudaMemsetAsync(n.d_prev, 0, sizeof(float) * (size_t)n.nimg * Hf * n.W, s));
     long long total = 0;
+    CoderPool pool;
+    pool.start(coders, n.nimg, n.nstep, false);
     for (int step = 0; step < nsteps; step++) {
         int cnt = 0;
         rc = wave_launch_step(n, step, n.d_prev, &cnt, s);
@@ -560,7 +630,7 @@ int pcx_wave_decode(const pcx_wave_net *net, pcx_coder *coder, long long *n_symb
         if (cnt > 0) {
             PCX_CUDA(cudaMemcpyAsync(g_pin.cdf[0], n.d_cdf, sizeof(int32_t) * (size_t)cnt * (n.nstep + 1), cudaMemcpyDeviceToHost, s));
             PCX_CUDA(cudaStreamSynchronize(s));
-            rc = pcx_coder_decodes(coder, g_pin.cdf[0], n.nstep, cnt, g_pin.lab[0]);
+            rc = pool.run(g_pin.cdf[0], nullptr, g_pin.lab[0], cnt / n.nimg);
             if (rc < 0) return rc;
             PCX_CUDA(cudaMemcpyAsync(n.d_prev, g_pin.lab[0], sizeof(float) * (size_t)cnt, cudaMemcpyHostToDevice, s));
             total += cnt;

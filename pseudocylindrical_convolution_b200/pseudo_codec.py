@@ -137,6 +137,21 @@ class EntEncoder(_EntBase):
             self.mcoder.end_encoder()
 
 
+    def encode_batch(self, data, code_names):
+        """data (nimg*npart, ngroup, h, w): the nimg images go through the wavefront together (native engine), each into
+        its own bitstream file - byte-identical to coding them one by one."""
+        with torch.no_grad():
+            self.apply(restart_entropy_network)
+            data = self.fill(data)
+            self.ctx2.setup_context(data.shape[3])
+            coders = [coder.coder(n) for n in code_names]
+            for c in coders:
+                c.start_encoder()
+            self.engine().encode(data, coders)
+            for c in coders:
+                c.end_encoder()
+
+
 class EntDecoder(_EntBase):
     """Inverse of EntEncoder: decodes (npart, ngroup, h, w) symbols from the bitstream (reference :117-160)."""
 
@@ -160,6 +175,17 @@ class EntDecoder(_EntBase):
             b = self.ipt(pout)
             code = (b[:self.npart, :, 2:-2, 2:-2] + self.bias).contiguous()
             return self.fill(code)
+
+
+    def decode_batch(self, h, w, code_names):
+        """inverse of EntEncoder.encode_batch: returns (nimg*npart, ngroup, h, w)"""
+        with torch.no_grad():
+            self.apply(restart_entropy_network)
+            self.ctx2.setup_context(w)
+            coders = [coder.coder(n) for n in code_names]
+            for c in coders:
+                c.start_decoder()
+            return self.fill(self.engine().decode(h, w, coders, torch.device(self.cuda)))
 
 
 class PseudoEncoder(nn.Module):
@@ -204,6 +230,12 @@ class PseudoEncoder(nn.Module):
             self.ent.start(code_name)
             self.ent(hcode_i)
 
+    def encode_batch(self, x, code_names):
+        """x (N, 3, H, W) -> N bitstream files; transforms and wavefront run batched on the device."""
+        with torch.no_grad():
+            assert x.shape[0] == len(code_names)
+            self.ent.encode_batch(self.symbols(x), code_names)
+
 
 class PseudoDecoder(nn.Module):
 
@@ -242,6 +274,15 @@ class PseudoDecoder(nn.Module):
             self.ent.start(code_name)
             hcode_i = self.ent(height // 128, width // 8)
             return self.reconstruct(hcode_i)
+
+
+def _decode_batch(self, code_names, height=512, width=1024):
+    """N bitstream files -> (N, 3, H, W) reconstructions (batched wavefront + batched synthesis transform)."""
+    with torch.no_grad():
+        return self.reconstruct(self.ent.decode_batch(height // 128, width // 8, code_names))
+
+
+PseudoDecoder.decode_batch = _decode_batch
 
 
 def img2tensor(img, device):

@@ -72,22 +72,30 @@ class WaveEngine:
         self.net, self.bufs, self._keep = net, bufs, (band, row, col, tw, items, d_order, convs)
         self._key = key
 
-    def encode(self, data, coder):
-        """data: (nimg*npart, G, h, W) symbols (already PseudoFill'ed); coder: started coder.coder."""
+    @staticmethod
+    def _handles(coders):
+        coders = coders if isinstance(coders, (list, tuple)) else [coders]
+        return (C.c_void_p * len(coders))(*[c._h for c in coders]), len(coders)
+
+    def encode(self, data, coders):
+        """data: (nimg*npart, G, h, W) symbols (already PseudoFill'ed); coders: one started coder.coder per image."""
         NN, G, h, W = data.shape
         nimg = NN // self.ent.npart
+        hs, nc = self._handles(coders)
+        assert nc == nimg, "one coder per image"
         with torch.cuda.device(data.device):
             self._build(h, W, nimg, data.device)
             n = C.c_longlong(0)
-            call("pcx_wave_encode", C.byref(self.net), C.c_void_p(data.data_ptr()), coder._h, C.byref(n),
+            call("pcx_wave_encode", C.byref(self.net), C.c_void_p(data.data_ptr()), hs, C.byref(n),
                  C.c_void_p(torch.cuda.current_stream().cuda_stream))
         return n.value
 
-    def decode(self, h, W, coder, device, nimg=1):
-        """returns the decoded symbol tensor (nimg*npart, G, h, W) as float"""
+    def decode(self, h, W, coders, device):
+        """returns the decoded symbol tensor (nimg*npart, G, h, W) as float; coders: one started decoder per image"""
+        hs, nimg = self._handles(coders)
         with torch.cuda.device(device):
             self._build(h, W, nimg, device)
             n = C.c_longlong(0)
-            call("pcx_wave_decode", C.byref(self.net), coder._h, C.byref(n), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            call("pcx_wave_decode", C.byref(self.net), hs, C.byref(n), C.c_void_p(torch.cuda.current_stream().cuda_stream))
             b = self.bufs[0]
             return (b[:nimg * self.ent.npart, :, 2:-2, 2:-2] + self.ent.bias).contiguous()

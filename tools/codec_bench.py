@@ -75,5 +75,22 @@ def main():
         print(json.dumps({"stage": name, "p50_ms": ts[1] * 1e3, "MP/s": H * W / 1e6 / ts[1], "bytes": os.path.getsize(path)}))
 
 
+    for N in (4, 8):
+        xs = torch.from_numpy(smooth_images(N, 3, H, W, seed=5)).to(dev)
+        names = [os.path.join(d, "b%d.bin" % i) for i in range(N)]
+        for name, fn in (("batched encode %d x 512x1024" % N, lambda: enc.encode_batch(xs, names)),
+                         ("batched decode %d x 512x1024" % N, lambda: dec.decode_batch(names, H, W))):
+            fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t0)
+            ts.sort()
+            print(json.dumps({"stage": name, "p50_ms": ts[1] * 1e3, "MP/s": N * H * W / 1e6 / ts[1]}))
+
+
 if __name__ == "__main__":
     main()
