@@ -232,6 +232,7 @@ typedef struct pcx_wave_layer {
 } pcx_wave_layer;
 typedef struct pcx_wave_net {
     int nlayers, nb, nimg, npart, G, h, W, pad, nstep, ng;
+    int cdf_rows;                                    /* capacity of d_cdf / d_lab in rows */
     float gmm_bias, gmm_total, gmm_beta, input_bias;
     const int *wl;                                   /* host, npart */
     const int *d_band, *d_row, *d_col;               /* mode-1 halo table (pcx_halo_table) */
@@ -243,6 +244,8 @@ typedef struct pcx_wave_net {
     float *d_params;                                 /* (nb, go_last, h*npart, W) * nimg extraction buffer */
     int *d_cdf;                                      /* (rows, nstep+1) int32 */
     float *d_prev;                                   /* (nimg, h*npart*W) symbols of the previous step */
+    int *d_lab;                                      /* (cdf_rows) int32 symbols in coding order (one-shot encoder) */
+    int *d_steptab;                                  /* 2*(steps+1) ints of scratch (one-shot encoder) */
     pcx_wave_layer layers[PCX_WAVE_MAX_LAYERS];
 } pcx_wave_net;
 int pcx_wave_steps(const pcx_wave_net *net);         /* h*npart + W + G - 2 */
@@ -250,6 +253,10 @@ int pcx_wave_steps(const pcx_wave_net *net);         /* h*npart + W + G - 2 */
  * nimg images advance through the wavefront together - same step count, nimg times the work per launch - and each
  * gets its own headerless bitstream, identical to coding it alone. */
 int pcx_wave_encode(const pcx_wave_net *net, const float *d_data, pcx_coder *const *coders, long long *n_symbols, void *stream);
+/* One-shot form of pcx_wave_encode (the encoder knows every symbol): each of the 12 layers is evaluated over the whole tensor
+ * in one launch with the per-scalar arithmetic of the stepwise form, the CDF rows are emitted in the stepwise coding order in
+ * chunks of at most cdf_rows rows and coded on host threads (one per image) behind the device.  Same bitstreams, byte for byte. */
+int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder *const *coders, long long *n_symbols, void *stream);
 /* Decodes every symbol of the nimg bitstreams; on return layers[0].in holds symbol + input_bias at every valid cell. */
 int pcx_wave_decode(const pcx_wave_net *net, pcx_coder *const *coders, long long *n_symbols, void *stream);
 

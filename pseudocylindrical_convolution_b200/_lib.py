@@ -31,10 +31,10 @@ class WaveLayer(C.Structure):
 
 class WaveNet(C.Structure):
     """struct pcx_wave_net (include/pcx.h)."""
-    _fields_ = ([(n, C.c_int) for n in ("nlayers", "nb", "nimg", "npart", "G", "h", "W", "pad", "nstep", "ng")] +
+    _fields_ = ([(n, C.c_int) for n in ("nlayers", "nb", "nimg", "npart", "G", "h", "W", "pad", "nstep", "ng", "cdf_rows")] +
                 [(n, C.c_float) for n in ("gmm_bias", "gmm_total", "gmm_beta", "input_bias")] +
                 [(n, C.c_void_p) for n in ("wl", "d_band", "d_row", "d_col", "d_tw", "d_items", "h_pstart", "d_order", "h_start",
-                                           "d_params", "d_cdf", "d_prev")] +
+                                           "d_params", "d_cdf", "d_prev", "d_lab", "d_steptab")] +
                 [("layers", WaveLayer * 16)])
 
 
@@ -82,6 +82,7 @@ PROTOTYPES = {
     "pcx_dextract_step": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _IP, _IP, _P]),
     "pcx_wave_steps": (_I, [C.POINTER(WaveNet)]),
     "pcx_wave_encode": (_I, [C.POINTER(WaveNet), _P, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), _P]),
+    "pcx_wave_encode_full": (_I, [C.POINTER(WaveNet), _P, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), _P]),
     "pcx_wave_decode": (_I, [C.POINTER(WaveNet), C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), _P]),
     "pcx_gmm_table": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _I, _P, _P, _P]),
     "pcx_gmm_nll": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),

@@ -10,3 +10,10 @@ CONV_IMPL = int(os.environ.get("PCX_CONV_IMPL", "0"))
 # native call), 0 = operator-by-operator Python loop shaped like the reference's EntEncoder / EntDecoder.  Same kernels,
 # bit-identical CDF tables and bitstreams.
 WAVE_IMPL = int(os.environ.get("PCX_WAVE_IMPL", "1"))
+
+# entropy ENCODER inside the native engine: 1 (default) = one-shot (pcx_wave_encode_full: every layer of the context model
+# over the whole symbol tensor in one launch, CDF rows emitted in coding order, host coder pipelined behind the device),
+# 0 = the stepwise loop (pcx_wave_encode).  Same per-scalar arithmetic, byte-identical bitstreams.
+WAVE_ENCODE_FULL = int(os.environ.get("PCX_WAVE_ENCODE_FULL", "1"))
+# rows (symbols) per image in one chunk of the one-shot encoder's CDF stream: the host codes chunk i while chunk i+1 is computed
+WAVE_CHUNK_ROWS = int(os.environ.get("PCX_WAVE_CHUNK_ROWS", str(1 << 17)))

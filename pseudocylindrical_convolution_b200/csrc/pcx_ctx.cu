@@ -35,18 +35,28 @@ inline int grid_for(i64 total, int threads)
 // entropy_ctx_pad_run2_forward_kernel (extension/entropy_ctx_pad_run2_cuda.cu:33-65)
 __global__ void ctx_pad_kernel(float *__restrict__ buf, Bands bands, const int *__restrict__ hband, const int *__restrict__ hrow,
                                const int *__restrict__ hcol, const float *__restrict__ htw, const int4 *__restrict__ items,
-                               int first, int nitems, int nrep, int cpn, int C, int h, int W, int pad, int psum)
+                               int first, int nitems, int nrep, int cpn, int C, int h, int W, int pad, int psum, int full, int kind)
 {
+    // full == 0: the items of the current plane window, channel group psum - plane (one wavefront step).
+    // full == 1: every channel group of every item (one-shot encoder); kind selects halo (0) or right-wrap (1) items,
+    //            because a wrap item of a halo row copies a halo cell and must run after it.
     i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    i64 total = (i64)nitems * cpn * nrep;
+    i64 total = (i64)nitems * cpn * nrep * (full ? C / cpn : 1);
     if (idx >= total) return;
     int it = (int)(idx % nitems);
     int cc = (int)((idx / nitems) % cpn);
     i64 n = idx / nitems / cpn;
     int4 I = items[first + it];
+    if (kind >= 0 && I.x != kind) return;
     const int npart = bands.npart;
     const i64 oh = h + 2 * pad, ow = W + 2 * pad;
-    i64 c = (i64)(psum - I.w) * cpn + cc;
+    int grp = psum - I.w;
+    if (full) {
+        const int G = C / cpn;
+        grp = (int)(n % G);
+        n /= G;
+    }
+    i64 c = (i64)grp * cpn + cc;
     if (I.x == 0) {
         int e = I.y, hr = I.z;
         int g = hr / (2 * pad), s = (hr / pad) % 2, r = hr % pad, x = e % W;
@@ -67,24 +77,40 @@ __global__ void ctx_pad_kernel(float *__restrict__ buf, Bands bands, const int *
 
 // ------------------------------------------------------------------------------------------------ masked conv
 // entropy_conv2_data_to_col_gpu_v3{,_act}_batch (extension/entropy_conv_cuda_v2.cu:237-290, :326-379)
-template <int GI>
+// FULL: every (cell, channel group) of the tensor in one launch, each scalar evaluated at its own step
+// psum = group + row + col - the same chains and tree as the stepwise form, hence the same bits.
+template <int GI, bool FULL>
 __global__ void __launch_bounds__(256) ctx_conv_kernel(const float *__restrict__ in, const float *__restrict__ weight,
                                                        const float *__restrict__ bias, const float *__restrict__ act,
                                                        float *__restrict__ out, const int *__restrict__ order, int first,
-                                                       int len, int nimg, int nscalars, int npart, int G, int go, int h,
-                                                       int W, int pad_in, int pad_out, int constrain, int psum)
+                                                       int len, int nimg, i64 nscalars, int npart, int G, int go, int h,
+                                                       int W, int pad_in, int pad_out, int constrain, int psum, Bands bands)
 {
     const int lane = threadIdx.x & 31;
-    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 wid = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (wid >= nscalars) return;
-    // scalar id -> (cell k, output-in-group og, batch-image pn), cell fastest (the reference's blockIdx order)
-    const int k = wid % len;
-    const int og = (wid / len) % go;
-    const int pn = wid / len / go;
+    int og, pn, tw, hp, tc;
+    if (FULL) {
+        // scalar id -> (col, global row, channel group, output-in-group, batch-image), col fastest
+        i64 r = wid;
+        tw = (int)(r % W); r /= W;
+        hp = (int)(r % ((i64)h * npart)); r /= (i64)h * npart;
+        tc = (int)(r % G); r /= G;
+        og = (int)(r % go);
+        pn = (int)(r / go);
+        if (tw >= bands.wl[hp / h]) return;
+        psum = tc + tw + hp;
+    } else {
+        // scalar id -> (cell k, output-in-group og, batch-image pn), cell fastest (the reference's blockIdx order)
+        const int k = (int)(wid % len);
+        og = (int)((wid / len) % go);
+        pn = (int)(wid / len / go);
+        const int hw = order[first + k];
+        tw = hw % W; hp = hw / W;
+        tc = psum - tw - hp;
+    }
     const int b = pn / nimg;
-    const int hw = order[first + k];
-    const int tw = hw % W, hp = hw / W, g = hp / h, th = hp % h;
-    const int tc = psum - tw - hp;
+    const int g = hp / h, th = hp % h;
     const int pout = tc * go + og;
     const int Ci = G * GI, Co = G * go;
     const i64 ih = h + 2 * pad_in, iw = W + 2 * pad_in;
@@ -126,6 +152,150 @@ __global__ void __launch_bounds__(256) ctx_conv_kernel(const float *__restrict__
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ masked conv, tiled form
+// Throughput form of the same arithmetic for the one-shot encoder.  A thread owns CPT cells (columns x, x+32, ...) of one
+// row for one (net image, channel group tc) and produces their GO = 3 outputs.  It evaluates the reference's 128 virtual
+// lanes one after the other - lane i = (m, kh, kw) is the chain acc = fma(in[k*GI+m], w[k*GI+m], acc) over the allowed groups
+// k in ascending order - and folds them in the reference's tree ([t]+=[t+64], [t]+=[t+32], shuffle-down 16..1) depth first, so
+// only a handful of partial sums are live.  Chain lengths depend on (tc, kh, kw) only: no divergence inside a block.  Each
+// input value is loaded once (coalesced across the warp) for three FMAs; the weights of the block's (net, tc) sit in shared
+// memory as one float4 per (channel, tap) and are read as warp-uniform 128-bit broadcasts.
+constexpr int CT_CPT = 4;          // cells per thread
+constexpr int CT_WARPS = 4;        // warps (= row tiles of 32*CPT columns) per block
+
+struct CtAcc { float v[CT_CPT][3]; };
+
+__device__ __forceinline__ CtAcc ct_zero()
+{
+    CtAcc a;
+#pragma unroll
+    for (int c = 0; c < CT_CPT; c++) a.v[c][0] = a.v[c][1] = a.v[c][2] = 0.f;
+    return a;
+}
+__device__ __forceinline__ CtAcc ct_add(const CtAcc &a, const CtAcc &b)
+{
+    CtAcc r;
+#pragma unroll
+    for (int c = 0; c < CT_CPT; c++)
+#pragma unroll
+        for (int o = 0; o < 3; o++) r.v[c][o] = __fadd_rn(a.v[c][o], b.v[c][o]);
+    return r;
+}
+
+struct CtCtx {
+    const float *in_cell;       // input at (channel 0, row, column of cell 0), this lane
+    const float4 *ws;           // shared weights [(ci * 25 + tap)] -> (og0, og1, og2, -)
+    i64 chs;                    // channel stride of the padded input
+    int iw, tc, G, c6;
+};
+
+template <int GI, int I>
+__device__ __forceinline__ CtAcc ct_chain(const CtCtx &x)
+{
+    CtAcc a = ct_zero();
+    if (I < 25 * GI) {
+        constexpr int kw = I % 5, kh = (I / 5) % 5, m = I / 25;
+        int nk = x.tc + 4 - kh - kw + x.c6;
+        nk = nk > x.G ? x.G : nk;
+        const float *ip = x.in_cell + (i64)m * x.chs + (kh - 2) * x.iw + (kw - 2);
+        const float4 *wp = x.ws + m * 25 + kh * 5 + kw;
+        for (int k = 0; k < nk; k++) {
+            const float4 w = *wp;
+#pragma unroll
+            for (int c = 0; c < CT_CPT; c++) {
+                const float v = ip[32 * c];
+                a.v[c][0] = __fmaf_rn(v, w.x, a.v[c][0]);
+                a.v[c][1] = __fmaf_rn(v, w.y, a.v[c][1]);
+                a.v[c][2] = __fmaf_rn(v, w.z, a.v[c][2]);
+            }
+            ip += (i64)GI * x.chs;
+            wp += GI * 25;
+        }
+    }
+    return a;
+}
+
+// value of virtual lane T after the two shared-memory folds: ([T] + [T+64]) + ([T+32] + [T+96]); dead lanes hold +0.0f
+template <int GI, int T>
+__device__ __forceinline__ CtAcc ct_leaf(const CtCtx &x)
+{
+    CtAcc lo = ct_add(ct_chain<GI, T>(x), ct_chain<GI, T + 64>(x));
+    CtAcc hi = ct_add(ct_chain<GI, T + 32>(x), ct_zero());
+    return ct_add(lo, hi);
+}
+// value of lane T after the shuffle-down steps 16 .. OFF
+template <int GI, int T, int OFF>
+struct CtTree {
+    static __device__ __forceinline__ CtAcc run(const CtCtx &x)
+    {
+        CtAcc a = CtTree<GI, T, OFF * 2>::run(x);
+        CtAcc b = CtTree<GI, T + OFF, OFF * 2>::run(x);
+        return ct_add(a, b);
+    }
+};
+template <int GI, int T>
+struct CtTree<GI, T, 32> {
+    static __device__ __forceinline__ CtAcc run(const CtCtx &x) { return ct_leaf<GI, T>(x); }
+};
+
+template <int GI>
+__global__ void __launch_bounds__(32 * CT_WARPS) ctx_conv_tiled_kernel(const float *__restrict__ in, const float *__restrict__ weight,
+                                                                       const float *__restrict__ bias, const float *__restrict__ act,
+                                                                       const float *__restrict__ addsrc, float *__restrict__ out,
+                                                                       int nimg, int npart, int G, int h, int W, int pad_in,
+                                                                       int pad_out, int constrain, Bands bands)
+{
+    extern __shared__ float4 ct_ws[];
+    const int tc = blockIdx.y, pn = blockIdx.z, b = pn / nimg;
+    const int Ci = G * GI, Co = G * 3;
+    // stage the weights of the three outputs of (net b, group tc): only the channel groups any chain can reach
+    int gmax = tc + 4 + (constrain == 6 ? 1 : 0);
+    gmax = gmax > G ? G : gmax;
+    const int nw = gmax * GI * 25;
+    for (int i = threadIdx.x; i < nw * 3; i += blockDim.x) {
+        const int og = i / nw, r = i % nw;
+        reinterpret_cast<float *>(ct_ws)[r * 4 + og] = weight[(((i64)b * Co + tc * 3 + og) * Ci) * 25 + r];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ntile = (W + 32 * CT_CPT - 1) / (32 * CT_CPT);
+    const int rt = blockIdx.x * CT_WARPS + warp;
+    const int Hf = h * npart;
+    if (rt >= Hf * ntile) return;
+    const int hp = rt / ntile, x0 = (rt % ntile) * 32 * CT_CPT;
+    const int g = hp / h, th = hp % h, wl = bands.wl[g];
+    if (x0 >= wl) return;
+    const i64 ih = h + 2 * pad_in, iw = W + 2 * pad_in;
+    const i64 qn = (i64)pn * npart + g;
+    // W is a multiple of 32*CPT (launcher), so every column of the tile lies inside the padded row; columns >= wl are
+    // computed on zero cells and discarded
+    const int tw0 = x0 + lane;
+    CtCtx x;
+    x.chs = ih * iw;
+    x.iw = (int)iw;
+    x.tc = tc;
+    x.G = G;
+    x.c6 = constrain == 6 ? 1 : 0;
+    x.ws = ct_ws;
+    x.in_cell = in + (qn * Ci * ih + th + pad_in) * iw + tw0 + pad_in;
+    CtAcc r = CtTree<GI, 0, 1>::run(x);
+    const i64 oh = h + 2 * pad_out, ow = W + 2 * pad_out;
+#pragma unroll
+    for (int c = 0; c < CT_CPT; c++) {
+        const int tw = tw0 + 32 * c;
+        if (tw >= wl) continue;
+#pragma unroll
+        for (int og = 0; og < 3; og++) {
+            const int pout = tc * 3 + og, bidx = b * Co + pout;
+            float sum = __fadd_rn(r.v[c][og], bias[bidx]);
+            if (act != nullptr && sum < 0.f) sum = __fmul_rn(sum, act[bidx]);
+            const i64 o = ((qn * Co + pout) * oh + th + pad_out) * ow + tw + pad_out;
+            if (addsrc != nullptr) sum = __fadd_rn(sum, addsrc[o]);
+            out[o] = sum;
+        }
+    }
+}
 
 // entropy_add_forward_kernel (extension/entropy_add_cuda.cu:25-44)
 __global__ void ctx_add_kernel(float *__restrict__ y, const float *__restrict__ x, const int *__restrict__ order, int first,
@@ -183,33 +353,24 @@ __global__ void dextract_kernel(const float *__restrict__ in, float *__restrict_
 // (extension/entropy_gmm_table_cuda.cu:29-56, :83-105, :136-153) in one launch, one thread per symbol.
 // Expression shapes follow the reference's SASS: float v, FMUL s2*(v-mu), IEEE float division, erff,
 // DFMA(erf, .5, .5), DFMA(f, w, ps) rounded to float per component, FMUL total*ps, DADD .5, truncation.
-__global__ void gmm_table_kernel(float *__restrict__ logit, float *__restrict__ delta, const float *__restrict__ mean, int n,
-                                 int ng, int nstep, float bias, float total, float beta, int form, float *__restrict__ cdf_f,
-                                 int *__restrict__ cdf_i)
+// w: mixture logits on entry, softmax weights on return; d: raw deltas on entry, clamped on return; c[0..nstep]: the table
+__device__ __forceinline__ void gmm_cdf_row(float *w, float *d, const float *mu, int ng, int nstep, float bias, float total,
+                                            float beta, int form, float *c)
 {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    float w[PCX_MAX_GAUSS], d[PCX_MAX_GAUSS], mu[PCX_MAX_GAUSS];
     float mval = -1e10f, psum = 0.f;
-    for (int i = 0; i < ng; i++) {
-        w[i] = logit[(i64)r * ng + i];
+    for (int i = 0; i < ng; i++)
         if (mval < w[i]) mval = w[i];
-    }
     for (int i = 0; i < ng; i++) {
         w[i] = exp(w[i] - mval);
         psum += w[i];
     }
     for (int i = 0; i < ng; i++) {
         w[i] = w[i] / psum;
-        logit[(i64)r * ng + i] = w[i];                  // in place, like the reference
-        float t = delta[(i64)r * ng + i];
+        float t = d[i];
         t = t < 0 ? beta : t + beta;
-        delta[(i64)r * ng + i] = t;
         d[i] = t;
-        mu[i] = mean[(i64)r * ng + i];
     }
     const float s2 = (float)(1. / sqrt(2.0));
-    float c[33];
     c[0] = 0.f;
     c[nstep] = (float)static_cast<int>(total);
     for (int pt = 1; pt < nstep; pt++) {
@@ -240,10 +401,100 @@ __global__ void gmm_table_kernel(float *__restrict__ logit, float *__restrict__ 
     }
     if (fb > 0.f)
         for (int i = midx; i < nstep; i++) c[i + 1] -= fb;
+}
+
+__global__ void gmm_table_kernel(float *__restrict__ logit, float *__restrict__ delta, const float *__restrict__ mean, int n,
+                                 int ng, int nstep, float bias, float total, float beta, int form, float *__restrict__ cdf_f,
+                                 int *__restrict__ cdf_i)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    float w[PCX_MAX_GAUSS], d[PCX_MAX_GAUSS], mu[PCX_MAX_GAUSS];
+    for (int i = 0; i < ng; i++) {
+        w[i] = logit[(i64)r * ng + i];
+        d[i] = delta[(i64)r * ng + i];
+        mu[i] = mean[(i64)r * ng + i];
+    }
+    float c[33];
+    gmm_cdf_row(w, d, mu, ng, nstep, bias, total, beta, form, c);
+    for (int i = 0; i < ng; i++) {
+        logit[(i64)r * ng + i] = w[i];                  // in place, like the reference
+        delta[(i64)r * ng + i] = d[i];
+    }
     for (int i = 0; i <= nstep; i++) {
         if (cdf_f) cdf_f[(i64)r * (nstep + 1) + i] = c[i];
         if (cdf_i) cdf_i[(i64)r * (nstep + 1) + i] = (int)c[i];
     }
+}
+
+// ------------------------------------------------------------------------------------------------ one-shot encoder kernels
+// DInput2 over the whole tensor: every valid cell of every channel group gets symbol + bias, in the nb replicas.
+__global__ void dinput_full_kernel(const float *__restrict__ sym, float *__restrict__ out, Bands bands, i64 total, int G, int h,
+                                   int W, int pad, float bias, int rep, i64 rep_stride)
+{
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;                       // total = nimg * npart * G * h * W, layout of the symbol tensor
+    i64 r = idx;
+    int tw = (int)(r % W); r /= W;
+    int th = (int)(r % h); r /= h;
+    int tc = (int)(r % G);
+    i64 n = r / G;                                  // image * npart + band
+    if (tw >= bands.wl[(int)(n % bands.npart)]) return;
+    i64 i = ((n * G + tc) * (h + 2 * pad) + th + pad) * (W + 2 * pad) + tw + pad;
+    float v = __fadd_rn(sym[idx], bias);
+    for (int j = 0; j < rep; j++) out[i + j * rep_stride] = v;
+}
+
+// EntropyAdd over the whole tensor (valid interior cells).
+__global__ void ctx_add_full_kernel(float *__restrict__ y, const float *__restrict__ x, Bands bands, i64 total, int C, int h, int W,
+                                    int pad)
+{
+    i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;                       // total = planes * C * h * W
+    i64 r = idx;
+    int tw = (int)(r % W); r /= W;
+    int th = (int)(r % h); r /= h;
+    i64 pc = r;                                     // plane * C + channel
+    i64 plane = pc / C;
+    if (tw >= bands.wl[(int)(plane % bands.npart)]) return;
+    i64 i = (pc * (h + 2 * pad) + th + pad) * (W + 2 * pad) + tw + pad;
+    y[i] = __fadd_rn(y[i], x[i]);
+}
+
+// DExtract2Batch + EntropyBatchGmmTable + DExtract2(label) for a range of wavefront steps, rows written in CODING order:
+// row = image * rows_per_image + (rowbase[s] - rowbase[s0]) + k, where k runs over the cell window of step s
+// (cell = order[wfirst[s] + k], channel group = s - row - col) - the order in which the stepwise loop feeds the coder.
+__global__ void gmm_ordered_kernel(const float *__restrict__ params, const float *__restrict__ data, const int *__restrict__ order,
+                                   const int *__restrict__ wfirst, const int *__restrict__ rowbase, int s0, int s1, int nimg,
+                                   int npart, int G, int go, int h, int W, int ng, int nstep, float bias, float total, float beta,
+                                   int *__restrict__ cdf_i, int *__restrict__ lab_i)
+{
+    const int per = rowbase[s1] - rowbase[s0];
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (i64)per * nimg) return;
+    const int img = (int)(t / per);
+    const int j = (int)(t % per) + rowbase[s0];
+    int lo = s0, hi = s1;                          // rowbase[lo] <= j < rowbase[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (rowbase[mid] <= j) lo = mid; else hi = mid;
+    }
+    const int s = lo, k = j - rowbase[lo];
+    const int hw = order[wfirst[s] + k];
+    const int tw = hw % W, hp = hw / W, g = hp / h, th = hp % h;
+    const int tc = s - tw - hp;
+    const int Co = G * go;
+    float w[PCX_MAX_GAUSS], d[PCX_MAX_GAUSS], mu[PCX_MAX_GAUSS];
+    for (int i = 0; i < ng; i++) {
+        const i64 cell = ((i64)tc * go + i) * h * W + (i64)th * W + tw;
+        w[i] = params[(((i64)(0 * nimg + img) * npart + g) * Co) * h * W + cell];
+        d[i] = params[(((i64)(1 * nimg + img) * npart + g) * Co) * h * W + cell];
+        mu[i] = params[(((i64)(2 * nimg + img) * npart + g) * Co) * h * W + cell];
+    }
+    float c[33];
+    gmm_cdf_row(w, d, mu, ng, nstep, bias, total, beta, 0, c);
+    for (int i = 0; i <= nstep; i++) cdf_i[t * (nstep + 1) + i] = (int)c[i];
+    lab_i[t] = (int)data[((((i64)img * npart + g) * G + tc) * h + th) * W + tw];
 }
 
 // entropy_gmm_forward_kernel (extension/entropy_gmm_cuda.cu:36-69), loss only
@@ -288,7 +539,7 @@ int pcx_ctx_pad_step(float *d_buf, int nrep, int npart, int G, int cpn, int h, i
     i64 total = (i64)nitems * cpn * nrep;
     ctx_pad_kernel<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(d_buf, b, d_band, d_row, d_col, d_tw,
                                                                            (const int4 *)d_items, h_pstart[st], nitems, nrep,
-                                                                           cpn, G * cpn, h, W, pad, psum);
+                                                                           cpn, G * cpn, h, W, pad, psum, 0, -1);
     PCX_LAUNCHED();
     return PCX_OK;
 }
@@ -310,12 +561,13 @@ int pcx_ctx_conv_step(const float *d_in, const float *d_weight, const float *d_b
     cudaStream_t s = (cudaStream_t)stream;
     const int threads = 256;
     int blocks = grid_for(nscalars * 32, threads);
+    Bands nob = {};
     if (gi == 1)
-        ctx_conv_kernel<1><<<blocks, threads, 0, s>>>(d_in, d_weight, d_bias, d_act, d_out, d_order, w.first, w.count, nimg,
-                                                      (int)nscalars, npart, G, go, h, W, pad_in, pad_out, constrain, psum);
+        ctx_conv_kernel<1, false><<<blocks, threads, 0, s>>>(d_in, d_weight, d_bias, d_act, d_out, d_order, w.first, w.count, nimg,
+                                                             nscalars, npart, G, go, h, W, pad_in, pad_out, constrain, psum, nob);
     else
-        ctx_conv_kernel<3><<<blocks, threads, 0, s>>>(d_in, d_weight, d_bias, d_act, d_out, d_order, w.first, w.count, nimg,
-                                                      (int)nscalars, npart, G, go, h, W, pad_in, pad_out, constrain, psum);
+        ctx_conv_kernel<3, false><<<blocks, threads, 0, s>>>(d_in, d_weight, d_bias, d_act, d_out, d_order, w.first, w.count, nimg,
+                                                             nscalars, npart, G, go, h, W, pad_in, pad_out, constrain, psum, nob);
     PCX_LAUNCHED();
     return PCX_OK;
 }
@@ -604,6 +856,140 @@ int pcx_wave_encode(const pcx_wave_net *net, const float *d_data, pcx_coder *con
     }
     for (auto &e : ev) cudaEventDestroy(e);
     if (n_symbols) *n_symbols = total;
+    return status;
+}
+
+// One-shot encoder: all symbols are known, so every layer is evaluated over the whole tensor in one launch
+// (12 x [halo, wrap, masked conv, add] instead of nsteps x 32 launches).  Each output scalar goes through the same FFMA chains
+// and fold tree as in the stepwise form, the halo cells are interpolated from the same final values, and the CDF rows are
+// emitted in the stepwise coding order - the bitstream is byte-identical (tests/test_gpu_codec.py).  The rows are produced in
+// chunks of whole steps; the host codes chunk i (one thread per image) while chunk i+1 is computed and copied.
+int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder *const *coders, long long *n_symbols, void *stream)
+{
+    int rc = wave_check(net);
+    if (rc < 0) return rc;
+    PCX_REQUIRE(d_data && coders, "null data / coders");
+    for (int i = 0; i < net->nimg; i++) PCX_REQUIRE(coders[i] != nullptr, "null coder for image %d", i);
+    const pcx_wave_net &n = *net;
+    PCX_REQUIRE(n.d_lab && n.d_steptab && n.cdf_rows > 0, "one-shot encoding needs d_lab, d_steptab and cdf_rows");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int Hf = n.h * n.npart, nsteps = pcx_wave_steps(net), nrep = n.nb * n.nimg;
+    Bands bands;
+    PCX_REQUIRE(make_bands(bands, n.wl, n.npart) == 0, "bad band description");
+
+    // per-step cell windows and the row prefix of the coding order
+    std::vector<int> tab(2 * (nsteps + 1));
+    int *wfirst = tab.data(), *rowbase = tab.data() + nsteps + 1;
+    int maxcnt = 0;
+    rowbase[0] = 0;
+    for (int st = 0; st < nsteps; st++) {
+        Window w = wave_window(n.h_start, st, n.G, Hf, n.W);
+        wfirst[st] = w.first;
+        rowbase[st + 1] = rowbase[st] + w.count;
+        if (w.count > maxcnt) maxcnt = w.count;
+    }
+    wfirst[nsteps] = 0;
+    const int cap = n.cdf_rows / n.nimg;                      // rows per image per chunk
+    PCX_REQUIRE(cap >= maxcnt, "cdf_rows %d too small for a step of %d rows x %d images", n.cdf_rows, maxcnt, n.nimg);
+    rc = ensure_pinned((size_t)n.cdf_rows, n.nstep);
+    if (rc < 0) return rc;
+    PCX_CUDA(cudaMemcpyAsync(n.d_steptab, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, s));
+
+    // ---- the network, layer by layer over the whole tensor
+    const i64 in_elems = (i64)nrep * n.npart * n.G * n.layers[0].gi * (n.h + 2 * n.pad) * (n.W + 2 * n.pad);
+    PCX_CUDA(cudaMemsetAsync(n.layers[0].in, 0, sizeof(float) * in_elems, s));
+    {
+        const i64 total = (i64)n.nimg * n.npart * n.G * n.h * n.W;
+        const i64 rep_stride = (i64)n.nimg * n.npart * n.G * (n.h + 2 * n.pad) * (n.W + 2 * n.pad);
+        dinput_full_kernel<<<grid_for(total, 256), 256, 0, s>>>(d_data, n.layers[0].in, bands, total, n.G, n.h, n.W, n.pad,
+                                                                n.input_bias, n.nb, rep_stride);
+        PCX_LAUNCHED();
+    }
+    const int nitems = n.h_pstart[Hf + n.W + n.pad - 1];
+    for (int L = 0; L < n.nlayers; L++) {
+        const pcx_wave_layer &l = n.layers[L];
+        const int Ci = n.G * l.gi, Co = n.G * l.go;
+        const i64 out_elems = (i64)nrep * n.npart * Co * (n.h + 2 * l.pad_out) * (n.W + 2 * l.pad_out);
+        PCX_CUDA(cudaMemsetAsync(l.out, 0, sizeof(float) * out_elems, s));
+        if (nitems > 0) {
+            const i64 total = (i64)nitems * Ci * nrep;
+            for (int kind = 0; kind < 2; kind++) {
+                ctx_pad_kernel<<<grid_for(total, 256), 256, 0, s>>>(l.in, bands, n.d_band, n.d_row, n.d_col, n.d_tw,
+                                                                    (const int4 *)n.d_items, 0, nitems, nrep, l.gi, Ci, n.h, n.W,
+                                                                    n.pad, 0, 1, kind);
+                PCX_LAUNCHED();
+            }
+        }
+        if (l.go == 3 && n.W % (32 * CT_CPT) == 0 && (l.gi == 1 || l.gi == 3)) {
+            // tiled throughput form, residual add fused into the store
+            const int ntile = n.W / (32 * CT_CPT);
+            dim3 grid((unsigned)ceil_div((i64)Hf * ntile, CT_WARPS), (unsigned)n.G, (unsigned)nrep);
+            const size_t smem = (size_t)Ci * 25 * sizeof(float4);
+            if (l.gi == 1)
+                ctx_conv_tiled_kernel<1><<<grid, 32 * CT_WARPS, smem, s>>>(l.in, l.weight, l.bias, l.act, l.add, l.out, n.nimg, n.npart, n.G,
+                                                                          n.h, n.W, n.pad, l.pad_out, l.constrain, bands);
+            else
+                ctx_conv_tiled_kernel<3><<<grid, 32 * CT_WARPS, smem, s>>>(l.in, l.weight, l.bias, l.act, l.add, l.out, n.nimg, n.npart, n.G,
+                                                                          n.h, n.W, n.pad, l.pad_out, l.constrain, bands);
+            PCX_LAUNCHED();
+            continue;
+        }
+        const i64 nscalars = (i64)nrep * l.go * n.G * Hf * n.W;
+        PCX_REQUIRE(nscalars * 32 / 256 < 0x7fffffffll, "tensor too large for one launch");
+        const int blocks = grid_for(nscalars * 32, 256);
+        if (l.gi == 1)
+            ctx_conv_kernel<1, true><<<blocks, 256, 0, s>>>(l.in, l.weight, l.bias, l.act, l.out, nullptr, 0, 0, n.nimg, nscalars, n.npart,
+                                                            n.G, l.go, n.h, n.W, n.pad, l.pad_out, l.constrain, 0, bands);
+        else if (l.gi == 3)
+            ctx_conv_kernel<3, true><<<blocks, 256, 0, s>>>(l.in, l.weight, l.bias, l.act, l.out, nullptr, 0, 0, n.nimg, nscalars, n.npart,
+                                                            n.G, l.go, n.h, n.W, n.pad, l.pad_out, l.constrain, 0, bands);
+        else
+            PCX_REQUIRE(false, "input channels per group must be 1 or 3 (got %d)", l.gi);
+        PCX_LAUNCHED();
+        if (l.add) {
+            const i64 total = (i64)nrep * n.npart * Co * n.h * n.W;
+            ctx_add_full_kernel<<<grid_for(total, 256), 256, 0, s>>>(l.out, l.add, bands, total, Co, n.h, n.W, l.pad_out);
+            PCX_LAUNCHED();
+        }
+    }
+
+    // ---- CDF rows in coding order, chunk by chunk, host coding pipelined behind the device
+    const pcx_wave_layer &last = n.layers[n.nlayers - 1];
+    cudaEvent_t ev[2];
+    for (auto &e : ev) PCX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CoderPool pool;
+    pool.start(coders, n.nimg, n.nstep, true);
+    int status = PCX_OK, per_chunk[2] = {0, 0}, s0 = 0, chunk = 0;
+    long long total_rows = 0;
+    auto code_chunk = [&](int b) -> int {
+        cudaError_t e = cudaEventSynchronize(ev[b]);
+        if (e != cudaSuccess) { pcx_set_error("cudaEventSynchronize -> %s", cudaGetErrorString(e)); return PCX_ECUDA; }
+        if (per_chunk[b] <= 0) return PCX_OK;
+        total_rows += (long long)per_chunk[b] * n.nimg;
+        return pool.run(g_pin.cdf[b], reinterpret_cast<int32_t *>(g_pin.lab[b]), nullptr, per_chunk[b]);
+    };
+    while (s0 < nsteps && status == PCX_OK) {
+        int s1 = s0 + 1;
+        while (s1 < nsteps && rowbase[s1 + 1] - rowbase[s0] <= cap) s1++;
+        const int per = rowbase[s1] - rowbase[s0], b = chunk & 1;
+        per_chunk[b] = per;
+        if (per > 0) {
+            const i64 rows = (i64)per * n.nimg;
+            gmm_ordered_kernel<<<grid_for(rows, 128), 128, 0, s>>>(last.out, d_data, n.d_order, n.d_steptab, n.d_steptab + nsteps + 1,
+                                                                   s0, s1, n.nimg, n.npart, n.G, last.go, n.h, n.W, n.ng, n.nstep,
+                                                                   n.gmm_bias, n.gmm_total, n.gmm_beta, n.d_cdf, n.d_lab);
+            PCX_LAUNCHED();
+            PCX_CUDA(cudaMemcpyAsync(g_pin.cdf[b], n.d_cdf, sizeof(int32_t) * (size_t)rows * (n.nstep + 1), cudaMemcpyDeviceToHost, s));
+            PCX_CUDA(cudaMemcpyAsync(g_pin.lab[b], n.d_lab, sizeof(int32_t) * (size_t)rows, cudaMemcpyDeviceToHost, s));
+        }
+        PCX_CUDA(cudaEventRecord(ev[b], s));
+        if (chunk >= 1) status = code_chunk(b ^ 1);           // code chunk c-1 while chunk c is computed and copied
+        s0 = s1;
+        chunk++;
+    }
+    if (status == PCX_OK && chunk >= 1) status = code_chunk((chunk - 1) & 1);
+    for (auto &e : ev) cudaEventDestroy(e);
+    if (n_symbols) *n_symbols = total_rows;
     return status;
 }
 

@@ -24,7 +24,8 @@ class WaveEngine:
 
     def _build(self, h, W, nimg, device):
         ent = self.ent
-        key = (h, W, nimg, str(device))
+        from . import config
+        key = (h, W, nimg, str(device), config.WAVE_CHUNK_ROWS)
         if self._key == key:
             return
         npart, G, pad, nb = ent.npart, ent.ngroup, 2, 3
@@ -54,10 +55,16 @@ class WaveEngine:
         net.d_order, net.h_start = _p(d_order), self._start.ctypes.data
         go_last = convs[-1].weight.shape[1] // G
         self.params = z(nb, go_last, Hf * nimg, W)
-        rows = nimg * min(Hf, W) * G + 16
+        # row capacity: at least one wavefront step (stepwise engine); the one-shot encoder emits chunks of up to WAVE_CHUNK_ROWS rows
+        # per image so that host coding of one chunk overlaps the device work and the copy of the next
+        ncell = h * sum(wl)
+        rows = nimg * max(min(Hf, W) * G + 16, min(ncell * G, config.WAVE_CHUNK_ROWS))
         self.cdf = torch.zeros((rows, 9), dtype=torch.int32, device=device)
+        self.lab = torch.zeros((rows,), dtype=torch.int32, device=device)
+        self.steptab = torch.zeros((2 * (Hf + W + G),), dtype=torch.int32, device=device)
         self.prev = z(nimg, Hf * W)
         net.d_params, net.d_cdf, net.d_prev = _p(self.params), _p(self.cdf), _p(self.prev)
+        net.cdf_rows, net.d_lab, net.d_steptab = rows, _p(self.lab), _p(self.steptab)
         for li, cv in enumerate(convs):
             l = net.layers[li]
             l.weight, l.bias = _p(cv.weight.data), _p(cv.bias.data)
@@ -86,7 +93,9 @@ class WaveEngine:
         with torch.cuda.device(data.device):
             self._build(h, W, nimg, data.device)
             n = C.c_longlong(0)
-            call("pcx_wave_encode", C.byref(self.net), C.c_void_p(data.data_ptr()), hs, C.byref(n),
+            from . import config
+            fn = "pcx_wave_encode_full" if config.WAVE_ENCODE_FULL else "pcx_wave_encode"
+            call(fn, C.byref(self.net), C.c_void_p(data.data_ptr()), hs, C.byref(n),
                  C.c_void_p(torch.cuda.current_stream().cuda_stream))
         return n.value
 

@@ -229,3 +229,32 @@ def test_batched_codec_equals_single_image_streams(codec, tmp_path):
     assert tuple(rec.shape) == (3, 3, H, W)
     one = dec(names[1], H, W)
     assert float((rec[1:2] - one).abs().max()) < 1e-6
+
+
+def test_one_shot_encoder_equals_stepwise_engine(codec, tmp_path):
+    """pcx_wave_encode_full evaluates every context-model layer over the whole symbol tensor in one launch and emits the CDF rows
+    in coding order; the stepwise engine runs the 204-step loop.  Same per-scalar arithmetic -> byte-identical bitstreams, for one
+    image, for a batch, and when the CDF stream is cut into many chunks."""
+    import torch
+    from pseudocylindrical_convolution_b200 import config
+    enc, dec, x, _ = codec
+    xs = torch.cat([x, torch.from_numpy(smooth_images(2, 3, H, W, seed=99)).to(x.device)]).contiguous()
+    sym = enc.symbols(xs)
+    streams = {}
+    try:
+        for full, chunk in ((0, 1 << 17), (1, 1 << 17), (1, 3000)):
+            config.WAVE_ENCODE_FULL, config.WAVE_CHUNK_ROWS = full, chunk
+            p1 = str(tmp_path / ("one_%d_%d.bin" % (full, chunk)))
+            enc.ent.start(p1)
+            enc.ent(sym[:16].clone())
+            names = [str(tmp_path / ("b%d_%d_%d.bin" % (i, full, chunk))) for i in range(3)]
+            enc.ent.encode_batch(sym.clone(), names)
+            streams[(full, chunk)] = [open(p1, "rb").read()] + [open(n, "rb").read() for n in names]
+    finally:
+        config.WAVE_ENCODE_FULL, config.WAVE_CHUNK_ROWS = 1, 1 << 17
+    ref = streams[(0, 1 << 17)]
+    assert len(ref[0]) > 1000 and ref[0] == ref[1]
+    for key, got in streams.items():
+        assert got == ref, "bitstreams of %s differ from the stepwise engine" % (key,)
+    got = dec.ent.decode_batch(H // 128, W // 8, names)
+    assert torch.equal(got, sym)

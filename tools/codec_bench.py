@@ -58,22 +58,24 @@ def main():
                           "TFLOP/s": 2 * 517752 * 0.8164 * mp * 1e6 / ms / 1e9}))
         del lat, sym, x
         torch.cuda.empty_cache()
-    H, W = 512, 1024
-    x = torch.from_numpy(smooth_images(1, 3, H, W, seed=1)).to(dev)
-    path = os.path.join(d, "img.bin")
-    for name, fn in (("full encode 512x1024 (transform + 204-step wavefront + host coder)", lambda: enc(x, path)),
-                     ("full decode 512x1024", lambda: dec(path, H, W))):
-        fn()
-        torch.cuda.synchronize()
-        ts = []
-        for _ in range(3):
-            t0 = time.perf_counter()
+    for H, W in ((512, 1024), (2048, 4096)):
+        x = torch.from_numpy(smooth_images(1, 3, H, W, seed=1)).to(dev)
+        path = os.path.join(d, "img.bin")
+        steps = H // 8 + W // 8 + 14 - 2
+        for name, fn in (("full encode %dx%d (transform + %d-step wavefront + host coder)" % (H, W, steps), lambda: enc(x, path)),
+                         ("full decode %dx%d" % (H, W), lambda: dec(path, H, W))):
             fn()
             torch.cuda.synchronize()
-            ts.append(time.perf_counter() - t0)
-        ts.sort()
-        print(json.dumps({"stage": name, "p50_ms": ts[1] * 1e3, "MP/s": H * W / 1e6 / ts[1], "bytes": os.path.getsize(path)}))
-
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t0)
+            ts.sort()
+            print(json.dumps({"stage": name, "p50_ms": ts[1] * 1e3, "MP/s": H * W / 1e6 / ts[1], "bytes": os.path.getsize(path)}), flush=True)
+        del x
+    H, W = 512, 1024
 
     for N in (4, 8):
         xs = torch.from_numpy(smooth_images(N, 3, H, W, seed=5)).to(dev)
