@@ -259,6 +259,11 @@ int pcx_wave_encode(const pcx_wave_net *net, const float *d_data, pcx_coder *con
 int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder *const *coders, long long *n_symbols, void *stream);
 /* Decodes every symbol of the nimg bitstreams; on return layers[0].in holds symbol + input_bias at every valid cell. */
 int pcx_wave_decode(const pcx_wave_net *net, pcx_coder *const *coders, long long *n_symbols, void *stream);
+/* pcx_wave_decode runs each wavefront step as ONE cooperative launch (DInput2, the masked layers with the halo taps interpolated
+ * on the fly, residual adds, DExtract2Batch + GMM table, separated by grid barriers; CDF rows and symbols cross PCIe through
+ * mapped pinned memory) when on != 0 (default), or as the launch-per-operator sequence when on == 0.  Same CDFs either way.
+ * Returns the previous setting. */
+int pcx_wave_set_fused(int on);
 
 /* ---- GMM ---------------------------------------------------------------------------------------------
  * EntropyGmmTableOp.forward_batch / forward (main.cpp:49-53 -> entropy_gmm_table_cuda.cu:107-185).

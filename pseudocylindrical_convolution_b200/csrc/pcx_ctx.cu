@@ -10,6 +10,8 @@
 #include <stdlib.h>
 #include <atomic>
 #include <thread>
+#include <chrono>
+#include <string.h>
 #include <vector>
 
 namespace {
@@ -518,6 +520,381 @@ __global__ void gmm_nll_kernel(const float *__restrict__ bottom_weight, const fl
     loss[index] = -log(sum_p + 0.0000001);
 }
 
+// ------------------------------------------------------------------------------------------------ fused wavefront step
+// One cooperative launch per wavefront step (decoder): DInput2 of the symbols decoded at the previous step, the 12 masked
+// layers (+ residual adds) at the cells of the current plane window, DExtract2Batch + GMM table - separated by grid-wide
+// barriers instead of kernel boundaries (1 launch per step instead of 32).  The halo of every layer input is never
+// materialised: a tap that falls on a halo / right-wrap cell evaluates the causal 2-tap interpolation (lerp2_ref, same
+// expression as ctx_pad_kernel) from the interior cells it is a function of.  Those cells lie on earlier-or-equal planes,
+// i.e. they are final when the tap is allowed by the mask - so every scalar sees the same input values as in
+// the stepwise operator path and runs the same chains and fold tree: bit-identical CDFs.  Activations written during the
+// launch are read with ld.global.cg (L2), never through L1.
+// in / out / add are the engine's own CHANNELS-LAST scratch [plane][row][col][cp]: the 16*gi input channels of a cell are one
+// 64*gi-byte run, so a lane that owns a filter tap fetches all its channel groups with a few 128-bit loads.
+struct StepLayer {
+    const float *weight, *bias, *act, *add, *in;
+    float *out;
+    int gi, pad_out, constrain, cp_in, cp_out;
+};
+struct StepNet {
+    int nlayers, nb, nimg, npart, G, h, W, pad, nstep, ng;
+    float gmm_bias, gmm_total, gmm_beta, input_bias;
+    Bands bands;
+    const int *hband, *hrow, *hcol, *order;
+    const float *htw;
+    float *sym_nchw;            // layers[0].in of the caller (NCHW, padded): receives symbol + input_bias for the Python side
+    const float *prev;          // symbols decoded at the previous step, (image, cell of the window) - mapped host memory
+    int *cdf;                   // CDF rows of this step, (image, cell of the window) x (nstep+1) - mapped host memory
+    unsigned *bar;              // grid barrier counter
+    unsigned long long *dbg;    // optional: globaltimer of block 0 at kernel entry, after every barrier and at exit (PCX_WAVE_TRACE)
+    StepLayer L[PCX_WAVE_MAX_LAYERS];
+};
+
+__device__ __forceinline__ void step_stamp(const StepNet &d, int step, int slot)
+{
+    if (d.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        d.dbg[(size_t)step * 32 + slot] = t;
+    }
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while ((int)(v - target) < 0);
+    }
+    __syncthreads();
+}
+
+struct StepTap {
+    const float *pa, *pb;       // mode 0: value = *pa; mode 1: lerp2(*pa, *pb, t); mode 2: lerp2(0, *pb, t); mode 3: 0
+    float t;
+    int mode;
+};
+
+// tap at row yi (relative to the band's first row, may be -pad..h+pad-1) and column xi (relative to the first valid column);
+// pa / pb point at channel 0 of the source cell(s) in the channels-last input
+__device__ __forceinline__ StepTap step_resolve(const StepNet &d, const float *in, i64 pn, int cp, int g, int yi, int xi)
+{
+    StepTap r;
+    r.pa = r.pb = in;
+    r.t = 0.f;
+    r.mode = 3;
+    const int h = d.h, W = d.W, pad = d.pad;
+    const i64 ih = h + 2 * pad, iw = W + 2 * pad;
+    const int wlg = d.bands.wl[g];
+    if (xi < 0) return r;                                        // left pad stays 0 (entropy_context_cuda.cu:85-103)
+    if (xi >= wlg) {                                             // right wrap: copy of the first pad columns of the same row
+        const int ph = g * h + yi;
+        if (xi >= wlg + pad || ph < 0 || ph >= h * d.npart) return r;
+        xi -= wlg;
+    }
+    if (yi >= 0 && yi < h) {
+        r.pa = r.pb = in + (((pn * d.npart + g) * ih + yi + pad) * iw + xi + pad) * cp;
+        r.mode = 0;
+        return r;
+    }
+    const int s = yi < 0 ? 0 : 1, rr = yi < 0 ? yi + pad : yi - h;
+    const int hr = (g * 2 + s) * pad + rr;
+    const int pg = d.hband[hr];
+    if (pg < 0) return r;                                        // pole rows stay 0
+    const i64 e = (i64)hr * W + xi;
+    const int q = d.hcol[e];
+    const float t = d.htw[e];
+    if (q < 0 && (double)t >= 1 - 1e-6) return r;                // no causal source: the cell stays 0
+    const float *srow = in + (((pn * d.npart + pg) * ih + d.hrow[hr] + pad) * iw + pad) * cp;
+    const int q1 = (q + 1 == d.bands.wl[pg]) ? 0 : q + 1;
+    r.pa = srow + (i64)(q < 0 ? 0 : q) * cp;
+    r.pb = srow + (i64)q1 * cp;
+    r.t = t;
+    r.mode = q < 0 ? 2 : 1;
+    return r;
+}
+
+// L2 load that keeps its program order among its kind (volatile asm), and a zero-instruction fence that makes seven loaded
+// values "used": together they force a batch of loads to be issued back to back before any dependent arithmetic.
+__device__ __forceinline__ float ld_cg_ordered(const float *p)
+{
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void reg_fence7(float (&a)[7])
+{
+    asm volatile("" : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]));
+}
+// 128-bit load, program-ordered among its kind; with on == 0 nothing is loaded and the result is +0.  L1-cached (.ca) on
+// purpose: inside one launch every scratch buffer is written in exactly one phase and read only in later ones, behind a grid
+// barrier with acquire semantics, and L1 starts clean at every launch - a cached line can never be stale, and the 5x5 windows
+// of neighbouring cells (handled by warps of the same block) overlap by two thirds.
+__device__ __forceinline__ float4 ld_cg_v4_ordered(const float *p, int on)
+{
+    float4 v;
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.s32 p, %5, 0;\nmov.f32 %0, 0f00000000;\nmov.f32 %1, 0f00000000;\nmov.f32 %2, 0f00000000;\n"
+        "mov.f32 %3, 0f00000000;\n@p ld.global.ca.v4.f32 {%0, %1, %2, %3}, [%4];\n}"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+        : "l"(p), "r"(on)
+        : "memory");
+    return v;
+}
+__device__ __forceinline__ void reg_fence_v4(float4 &a, float4 &b)
+{
+    asm volatile("" : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w), "+f"(b.x), "+f"(b.y), "+f"(b.z), "+f"(b.w));
+}
+
+// The block's share of a step: one (net image pn, plane) pair and a run of that plane's cells.  All cells of a plane carry
+// the same channel group tc = step - plane, so the three output rows of (net, tc) are the only weights the block needs:
+// they are staged in shared memory with cp.async one layer AHEAD (weights do not depend on the grid barrier).
+struct StepChunk { int pn, plane, cell0, ncell; };
+
+constexpr int STEP_THREADS = 256;
+
+__device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// rows of outputs tc*3 .. tc*3+2 of net b, channel groups < gmax: smem[og * wstride + r], r = ci * 25 + tap
+__device__ __forceinline__ void step_stage_weights(const StepNet &d, const StepLayer &l, int b, int tc, float *smem, int wstride)
+{
+    const int Ci = d.G * l.gi, Co = d.G * 3;
+    int gmax = tc + 4 + (l.constrain == 6 ? 1 : 0);
+    gmax = gmax > d.G ? d.G : gmax;
+    const int nw = gmax * l.gi * 25;
+    for (int i = threadIdx.x; i < nw * 3; i += blockDim.x) {
+        const int og = i / nw, r = i % nw;
+        cp_async4(smem + og * wstride + r, l.weight + (((i64)b * Co + tc * 3 + og) * Ci) * 25 + r);
+    }
+    // bias and PReLU slope of the three outputs behind the weight rows
+    if (threadIdx.x < 3) cp_async4(smem + 3 * wstride + threadIdx.x, l.bias + b * Co + tc * 3 + threadIdx.x);
+    else if (threadIdx.x < 6 && l.act != nullptr) cp_async4(smem + 3 * wstride + threadIdx.x, l.act + b * Co + tc * 3 + threadIdx.x - 3);
+}
+
+// One warp per cell.  Lane = filter tap (kh, kw) (25 live lanes); it runs the GI chains of its tap - the reference's virtual
+// lanes m*25 + tap - over the allowed channel groups in ascending order, 8 groups per batch of 128-bit loads.  The chain sums
+// are then moved to the virtual-lane positions (lane t takes lanes t, t+32, t+64 of the reference block) and folded exactly
+// like the reference: [t]+=[t+64], [t]+=[t+32], shuffle-down 16..1.
+template <int GI>
+__device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLayer &l, int step, const StepChunk &ch, const int *start,
+                                                const float *ws, int wstride)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int G = d.G, h = d.h, W = d.W;
+    const int cp = l.cp_in;
+    constexpr int NQ = 2 * GI;                                  // float4 per batch of 8 channel groups
+    const int c6 = l.constrain == 6 ? 1 : 0;
+    const int pn = ch.pn, tc = step - ch.plane;
+    const int first = start[ch.plane] + ch.cell0;
+    const bool live = lane < 25;
+    const int kw = lane % 5, kh = (lane / 5) % 5;
+    int nk_tap = live ? tc + 4 - kh - kw + c6 : 0;
+    nk_tap = nk_tap > G ? G : (nk_tap < 0 ? 0 : nk_tap);
+    int gmax = tc + 4 + c6;                                     // longest chain of the block (tap 0,0)
+    gmax = gmax > G ? G : gmax;
+    const float *wl_ = ws + kh * 5 + kw;
+    for (int k = warp; k < ch.ncell; k += nwarp) {
+        const int hw = d.order[first + k];
+        const int tw = hw % W, hp = hw / W, g = hp / h, th = hp % h;
+        StepTap tp;
+        tp.pa = tp.pb = l.in;
+        tp.t = 0.f;
+        tp.mode = 3;
+        if (live) tp = step_resolve(d, l.in, pn, cp, g, th + kh - 2, tw + kw - 2);
+        const int nk = tp.mode == 3 ? 0 : nk_tap;               // a zero input leaves the chains at +0.0f
+        // residual source of the three outputs: final since two phases ago, fetched now so that the epilogue waits for nothing
+        const i64 o = ((((i64)pn * d.npart + g) * (h + 2 * l.pad_out) + th + l.pad_out) * (W + 2 * l.pad_out) + tw + l.pad_out) * l.cp_out + tc * 3;
+        float addv[3] = {0.f, 0.f, 0.f};
+        if (l.add != nullptr && lane < 3) addv[0] = __ldcg(l.add + o + lane);
+        float acc[GI][3];
+#pragma unroll
+        for (int m = 0; m < GI; m++) acc[m][0] = acc[m][1] = acc[m][2] = 0.f;
+        for (int c0 = 0; c0 < gmax; c0 += 8) {
+            const int on = nk > c0;
+            float4 xa[NQ], xb[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; q++) xa[q] = ld_cg_v4_ordered(tp.pa + c0 * GI + 4 * q, on && tp.mode != 2);
+#pragma unroll
+            for (int q = 0; q < NQ; q++) xb[q] = ld_cg_v4_ordered(tp.pb + c0 * GI + 4 * q, on && tp.mode != 0);
+            // every activation load of the batch is in flight before the first FFMA can wait on one
+#pragma unroll
+            for (int q = 0; q < NQ; q += 2) {
+                reg_fence_v4(xa[q], xa[q + 1]);
+                reg_fence_v4(xb[q], xb[q + 1]);
+            }
+            float va[8 * GI], vb[8 * GI];
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                va[4 * q] = xa[q].x; va[4 * q + 1] = xa[q].y; va[4 * q + 2] = xa[q].z; va[4 * q + 3] = xa[q].w;
+                vb[4 * q] = xb[q].x; vb[4 * q + 1] = xb[q].y; vb[4 * q + 2] = xb[q].z; vb[4 * q + 3] = xb[q].w;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const bool act_k = c0 + u < nk;
+                const float *w = wl_ + (act_k ? (c0 + u) * GI * 25 : 0);
+#pragma unroll
+                for (int m = 0; m < GI; m++) {
+                    const float a = va[u * GI + m];             // +0 when mode == 2 (load predicated off)
+                    const float v = tp.mode == 0 ? a : lerp2_ref(a, vb[u * GI + m], tp.t);
+                    acc[m][0] = act_k ? __fmaf_rn(v, w[m * 25], acc[m][0]) : acc[m][0];
+                    acc[m][1] = act_k ? __fmaf_rn(v, w[m * 25 + wstride], acc[m][1]) : acc[m][1];
+                    acc[m][2] = act_k ? __fmaf_rn(v, w[m * 25 + 2 * wstride], acc[m][2]) : acc[m][2];
+                }
+            }
+        }
+        // chain (m, tap) = reference lane i = m*25 + tap; lane t now collects lanes t, t+32, t+64
+        float sum[3];
+#pragma unroll
+        for (int og = 0; og < 3; og++) {
+            float v0, v1 = 0.f, v2 = 0.f;
+            if (GI == 1) {
+                v0 = acc[0][og];                                // lanes >= 25 hold +0
+            } else {
+                const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
+                const float a0 = __shfl_sync(0xffffffffu, acc[0][og], i0 % 25);
+                const float a1 = __shfl_sync(0xffffffffu, acc[GI > 1 ? 1 : 0][og], i0 % 25);
+                v0 = i0 < 25 ? a0 : a1;
+                const float b1 = __shfl_sync(0xffffffffu, acc[GI > 1 ? 1 : 0][og], i1 % 25);
+                const float b2 = __shfl_sync(0xffffffffu, acc[GI > 2 ? 2 : 0][og], i1 % 25);
+                v1 = i1 < 50 ? b1 : b2;
+                const float c2 = __shfl_sync(0xffffffffu, acc[GI > 2 ? 2 : 0][og], i2 % 25);
+                v2 = i2 < 75 ? c2 : 0.f;
+            }
+            const float s0 = __fadd_rn(v0, v2);                 // [t] += [t+64]
+            const float s1 = __fadd_rn(v1, 0.f);
+            sum[og] = __fadd_rn(s0, s1);                        // [t] += [t+32]
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+            for (int og = 0; og < 3; og++) sum[og] = __fadd_rn(sum[og], __shfl_down_sync(0xffffffffu, sum[og], off));
+        addv[1] = __shfl_sync(0xffffffffu, addv[0], 1);
+        addv[2] = __shfl_sync(0xffffffffu, addv[0], 2);
+        if (lane == 0) {
+#pragma unroll
+            for (int og = 0; og < 3; og++) {
+                float v = __fadd_rn(sum[og], ws[3 * wstride + og]);
+                if (l.act != nullptr && v < 0.f) v = __fmul_rn(v, ws[3 * wstride + 3 + og]);
+                if (l.add != nullptr) v = __fadd_rn(v, addv[og]);
+                l.out[o + og] = v;
+            }
+        }
+    }
+}
+
+// run `id` of the step: every (net image, plane) pair of the window is cut into runs of at most S cells
+__device__ __forceinline__ StepChunk step_chunk_of(const int *__restrict__ start, int id, int p0, int np, int S, int nrep)
+{
+    StepChunk c = {0, p0, 0, 0};
+    for (int q = p0; q < p0 + np; q++) {
+        const int cells = start[q + 1] - start[q];
+        const int nrun = (cells + S - 1) / S;
+        if (id < nrun * nrep) {
+            const int run = id % nrun;
+            c.pn = id / nrun; c.plane = q; c.cell0 = run * S;
+            c.ncell = cells - run * S < S ? cells - run * S : S;
+            return c;
+        }
+        id -= nrun * nrep;
+    }
+    return c;
+}
+
+// start: device copy of the plane prefix of `order`; planes [p0, p0 + np) form the window of this step, cut into nchunk runs
+// (step_chunk_of); block i works on runs i, i + gridDim.x, ...  For every (layer, run) item the three weight rows are staged
+// in one of two shared-memory buffers while the previous item is being computed.
+__global__ void __launch_bounds__(STEP_THREADS) wave_step_kernel(const __grid_constant__ StepNet d, const int *__restrict__ start,
+                                                                 int step, int p0, int np, int S, int nchunk, int pfirst, int pcount,
+                                                                 unsigned bar_base)
+{
+    extern __shared__ float step_ws[];                // 2 buffers of 3 * wstride weights + 8 (bias, slope)
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    const int h = d.h, W = d.W, pad = d.pad, G = d.G, nrep = d.nb * d.nimg;
+    const int wstride = G * 3 * 25;
+    unsigned target = bar_base;
+    step_stamp(d, step, 0);
+    const int first = start[p0], count = start[p0 + np] - start[p0];
+    const int nmy = blockIdx.x < nchunk ? (nchunk - 1 - blockIdx.x) / gridDim.x + 1 : 0;      // my runs per layer
+    const int nitems = nmy * d.nlayers;
+    if (nitems > 0) {
+        const StepChunk c0 = step_chunk_of(start, blockIdx.x, p0, np, S, nrep);
+        step_stage_weights(d, d.L[0], c0.pn / d.nimg, step - c0.plane, step_ws, wstride);
+    }
+    cp_async_commit();
+    // ---- DInput2: the symbols decoded at step - 1 enter the padded input (3 replicas)
+    if (pcount > 0) {
+        const i64 ih = h + 2 * pad, iw = W + 2 * pad;
+        const int cp0 = d.L[0].cp_in;
+        const i64 rep_stride = (i64)d.nimg * d.npart * ih * iw * cp0;
+        float *out = const_cast<float *>(d.L[0].in);
+        for (int t = gtid; t < pcount * d.nimg; t += nthr) {
+            const int k = t % pcount, n = t / pcount;
+            const int hw = d.order[pfirst + k];
+            const int tw = hw % W, hp = hw / W, g = hp / h, th = hp % h;
+            const int tc = step - 1 - tw - hp;
+            const float v = __fadd_rn(d.prev[t], d.input_bias);
+            const i64 i = ((((i64)n * d.npart + g) * ih + th + pad) * iw + tw + pad) * cp0 + tc;
+            for (int j = 0; j < d.nb; j++) out[i + j * rep_stride] = v;
+            d.sym_nchw[((((i64)n * d.npart + g) * G + tc) * ih + th + pad) * iw + tw + pad] = v;
+        }
+    }
+    target += gridDim.x;
+    grid_barrier(d.bar, target);
+    step_stamp(d, step, 1);
+    // ---- the masked layers
+    int it = 0;
+    for (int L = 0; L < d.nlayers; L++) {
+        for (int ci = 0; ci < nmy; ci++, it++) {
+            const StepChunk ch = step_chunk_of(start, blockIdx.x + ci * gridDim.x, p0, np, S, nrep);
+            if (ci > 0) __syncthreads();               // every warp is done with item it-1: its buffer may be refilled
+            if (it + 1 < nitems) {
+                const int nci = ci + 1 < nmy ? ci + 1 : 0, nL = ci + 1 < nmy ? L : L + 1;
+                const StepChunk nc = step_chunk_of(start, blockIdx.x + nci * gridDim.x, p0, np, S, nrep);
+                step_stage_weights(d, d.L[nL], nc.pn / d.nimg, step - nc.plane, step_ws + ((it + 1) & 1) * (3 * wstride + 8), wstride);
+            }
+            cp_async_commit();
+            cp_async_wait<1>();                        // this item's rows have landed; the next item's may still be in flight
+            __syncthreads();
+            const float *ws = step_ws + (it & 1) * (3 * wstride + 8);
+            if (d.L[L].gi == 1) step_conv_phase<1>(d, d.L[L], step, ch, start, ws, wstride);
+            else step_conv_phase<3>(d, d.L[L], step, ch, start, ws, wstride);
+        }
+        target += gridDim.x;
+        grid_barrier(d.bar, target);
+        step_stamp(d, step, 2 + L);
+    }
+    cp_async_wait<0>();
+    // ---- DExtract2Batch + GMM table, rows (image, cell of the window)
+    const StepLayer &last = d.L[d.nlayers - 1];
+    for (int t = gtid; t < count * d.nimg; t += nthr) {
+        const int k = t % count, img = t / count;
+        const int hw = d.order[first + k];
+        const int tw = hw % W, hp = hw / W, g = hp / h, th = hp % h;
+        const int tc = step - tw - hp;
+        float w[PCX_MAX_GAUSS], dl[PCX_MAX_GAUSS], mu[PCX_MAX_GAUSS];
+        float pv[9];
+#pragma unroll
+        for (int q = 0; q < 9; q++) {                     // 3 nets x 3 components, all loads in flight together
+            const int net = q / 3, i = q % 3;
+            pv[q] = i < d.ng ? __ldcg(last.out + ((((i64)(net * d.nimg + img) * d.npart + g) * h + th) * W + tw) * last.cp_out + tc * 3 + i) : 0.f;
+        }
+        for (int i = 0; i < d.ng && i < 3; i++) { w[i] = pv[i]; dl[i] = pv[3 + i]; mu[i] = pv[6 + i]; }
+        float c[33];
+        gmm_cdf_row(w, dl, mu, d.ng, d.nstep, d.gmm_bias, d.gmm_total, d.gmm_beta, 0, c);
+        for (int i = 0; i <= d.nstep; i++) d.cdf[(i64)t * (d.nstep + 1) + i] = (int)c[i];
+    }
+    step_stamp(d, step, 2 + d.nlayers);
+}
+
 }  // namespace
 
 extern "C" {
@@ -747,8 +1124,9 @@ int ensure_pinned(size_t rows, int nstep)
     for (int i = 0; i < 2; i++) {
         if (g_pin.cdf[i]) cudaFreeHost(g_pin.cdf[i]);
         if (g_pin.lab[i]) cudaFreeHost(g_pin.lab[i]);
-        PCX_CUDA(cudaHostAlloc((void **)&g_pin.cdf[i], rows * (nstep + 1) * sizeof(int32_t), cudaHostAllocDefault));
-        PCX_CUDA(cudaHostAlloc((void **)&g_pin.lab[i], rows * sizeof(float), cudaHostAllocDefault));
+        // mapped: the fused decoder step writes CDF rows / reads symbols through these buffers directly (zero-copy)
+        PCX_CUDA(cudaHostAlloc((void **)&g_pin.cdf[i], rows * (nstep + 1) * sizeof(int32_t), cudaHostAllocMapped | cudaHostAllocPortable));
+        PCX_CUDA(cudaHostAlloc((void **)&g_pin.lab[i], rows * sizeof(float), cudaHostAllocMapped | cudaHostAllocPortable));
     }
     g_pin.rows = rows;
     return PCX_OK;
@@ -993,6 +1371,173 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
     return status;
 }
 
+static std::atomic<int> g_wave_fused{1};
+static unsigned *g_bar = nullptr;
+static float *g_step_scratch = nullptr;
+static size_t g_step_scratch_bytes = 0;
+
+int pcx_wave_set_fused(int on)
+{
+    return g_wave_fused.exchange(on != 0 ? 1 : 0);
+}
+
+// Decoder loop on the fused step kernel: per step ONE cooperative launch, a stream synchronisation, the host range decoder
+// (one thread per image); CDF rows and decoded symbols cross PCIe through mapped pinned memory, no copy calls.
+static int wave_decode_fused(const pcx_wave_net &n, pcx_coder *const *coders, long long *n_symbols, cudaStream_t s)
+{
+    const int Hf = n.h * n.npart, nsteps = pcx_wave_steps(&n), nrep = n.nb * n.nimg;
+    const size_t max_rows = (size_t)n.nimg * (size_t)(Hf < n.W ? Hf : n.W) * n.G + 16;
+    int rc = ensure_pinned(max_rows, n.nstep);
+    if (rc < 0) return rc;
+    if (g_bar == nullptr) PCX_CUDA(cudaMalloc((void **)&g_bar, 64));
+    PCX_CUDA(cudaMemsetAsync(g_bar, 0, 64, s));
+    StepNet d;
+    d.nlayers = n.nlayers; d.nb = n.nb; d.nimg = n.nimg; d.npart = n.npart; d.G = n.G; d.h = n.h; d.W = n.W; d.pad = n.pad;
+    d.nstep = n.nstep; d.ng = n.ng;
+    d.gmm_bias = n.gmm_bias; d.gmm_total = n.gmm_total; d.gmm_beta = n.gmm_beta; d.input_bias = n.input_bias;
+    PCX_REQUIRE(make_bands(d.bands, n.wl, n.npart) == 0, "bad band description");
+    d.hband = n.d_band; d.hrow = n.d_row; d.hcol = n.d_col; d.htw = n.d_tw; d.order = n.d_order;
+    float *dev_prev = nullptr;
+    int *dev_cdf = nullptr;
+    PCX_CUDA(cudaHostGetDevicePointer((void **)&dev_prev, g_pin.lab[0], 0));
+    PCX_CUDA(cudaHostGetDevicePointer((void **)&dev_cdf, g_pin.cdf[0], 0));
+    d.prev = dev_prev; d.cdf = dev_cdf; d.bar = g_bar;
+    // PCX_WAVE_TRACE=<file>: per-step device timestamps (block 0) + host wall clock of the loop, written as text
+    const char *trace_path = getenv("PCX_WAVE_TRACE");
+    unsigned long long *h_dbg = nullptr;
+    std::vector<double> host_us;
+    d.dbg = nullptr;
+    if (trace_path) {
+        PCX_CUDA(cudaHostAlloc((void **)&h_dbg, sizeof(unsigned long long) * 32 * (size_t)nsteps, cudaHostAllocMapped));
+        memset(h_dbg, 0, sizeof(unsigned long long) * 32 * (size_t)nsteps);
+        PCX_CUDA(cudaHostGetDevicePointer((void **)&d.dbg, h_dbg, 0));
+        host_us.resize(3 * (size_t)nsteps);
+    }
+    // channels-last scratch: input of layer 0 (cp = 8*ceil(G/8)*gi0) and one output per layer (cp = 8*ceil(G/8)*3)
+    const int G8 = (n.G + 7) / 8 * 8;
+    const i64 planes = (i64)nrep * n.npart;
+    const i64 in_elems = planes * (n.h + 2 * n.pad) * (n.W + 2 * n.pad);
+    std::vector<i64> off(n.nlayers + 2);
+    off[0] = 0;
+    off[1] = in_elems * G8 * n.layers[0].gi;
+    for (int L = 0; L < n.nlayers; L++)
+        off[L + 2] = off[L + 1] + planes * (n.h + 2 * n.layers[L].pad_out) * (n.W + 2 * n.layers[L].pad_out) * G8 * 3;
+    const size_t need_bytes = sizeof(float) * (size_t)off[n.nlayers + 1] + 256;
+    if (need_bytes > g_step_scratch_bytes) {
+        if (g_step_scratch) cudaFree(g_step_scratch);
+        g_step_scratch = nullptr;
+        g_step_scratch_bytes = 0;
+        PCX_CUDA(cudaMalloc((void **)&g_step_scratch, need_bytes));
+        g_step_scratch_bytes = need_bytes;
+    }
+    PCX_CUDA(cudaMemsetAsync(g_step_scratch, 0, need_bytes, s));
+    for (int L = 0; L < n.nlayers; L++) {
+        const pcx_wave_layer &l = n.layers[L];
+        StepLayer &sl = d.L[L];
+        sl.weight = l.weight; sl.bias = l.bias; sl.act = l.act;
+        sl.in = g_step_scratch + off[L];
+        sl.out = g_step_scratch + off[L + 1];
+        sl.add = nullptr;
+        if (l.add) {
+            for (int M = 0; M < L; M++)
+                if (n.layers[M].out == l.add) sl.add = g_step_scratch + off[M + 1];
+            PCX_REQUIRE(sl.add != nullptr, "layer %d: the residual source must be the output of an earlier layer", L);
+            PCX_REQUIRE(n.layers[L].pad_out == n.pad, "layer %d: residual add on an unpadded output", L);
+        }
+        sl.gi = l.gi; sl.pad_out = l.pad_out; sl.constrain = l.constrain;
+        sl.cp_in = G8 * l.gi; sl.cp_out = G8 * 3;
+        PCX_REQUIRE(L == 0 || (l.in == n.layers[L - 1].out && l.gi == 3 && n.layers[L - 1].pad_out == n.pad),
+                    "layer %d must read the padded output of layer %d", L, L - 1);
+    }
+    d.sym_nchw = n.layers[0].in;
+    PCX_CUDA(cudaMemsetAsync(n.layers[0].in, 0, sizeof(float) * (size_t)nrep * n.npart * n.G * (n.h + 2 * n.pad) * (n.W + 2 * n.pad), s));
+
+    const int threads = STEP_THREADS;
+    const size_t smem = sizeof(float) * 2 * (3 * (size_t)n.G * 3 * 25 + 8);
+    PCX_CUDA(cudaFuncSetAttribute(wave_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PCX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wave_step_kernel, threads, smem));
+    PCX_REQUIRE(per_sm >= 1, "wave_step_kernel does not fit on an SM");
+    const int max_grid = pcx_sm_count() * per_sm;
+    const int nplanes = Hf + n.W - 1;
+    int *d_start = nullptr;
+    PCX_CUDA(cudaMalloc((void **)&d_start, sizeof(int) * (size_t)(Hf + n.W)));
+    PCX_CUDA(cudaMemcpyAsync(d_start, n.h_start, sizeof(int) * (size_t)(Hf + n.W), cudaMemcpyHostToDevice, s));
+
+    CoderPool pool;
+    pool.start(coders, n.nimg, n.nstep, false);
+    long long total = 0;
+    unsigned bar_base = 0;
+    int pfirst = 0, pcount = 0;
+    for (int step = 0; step < nsteps; step++) {
+        int p0 = step - n.G + 1 < 0 ? 0 : step - n.G + 1;
+        int p1 = step < nplanes - 1 ? step + 1 : nplanes;                  // planes [p0, p1) (entropy_conv_cuda_v2.cu:389-391)
+        if (p0 > p1) p0 = p1;
+        int np = p1 - p0;
+        int first = n.h_start[p0], count = n.h_start[p1] - n.h_start[p0];
+        // runs of at most S cells per (net image, plane); block i takes runs i, i + grid, ...  S (a multiple of the warps per
+        // block) minimises rounds-per-block x cells-per-warp, the critical path of a layer
+        const int wpb = threads / 32;
+        int maxcells = 1;
+        for (int q = p0; q < p1; q++) maxcells = n.h_start[q + 1] - n.h_start[q] > maxcells ? n.h_start[q + 1] - n.h_start[q] : maxcells;
+        int S = wpb, nchunk = 0;
+        long best = -1;
+        for (int cand = wpb; cand < maxcells + wpb; cand += wpb) {
+            int chunks = 0;
+            for (int q = p0; q < p1; q++) chunks += nrep * ceil_div(n.h_start[q + 1] - n.h_start[q], cand);
+            const long cost = (long)ceil_div(chunks, max_grid) * (cand / wpb);
+            if (best < 0 || cost < best) { best = cost; S = cand; nchunk = chunks; }
+        }
+        int grid = nchunk < max_grid ? nchunk : max_grid;
+        if (grid < 1) grid = 1;
+        const int *dstart = d_start;
+        void *args[] = {(void *)&d, (void *)&dstart, (void *)&step, (void *)&p0, (void *)&np, (void *)&S, (void *)&nchunk, (void *)&pfirst,
+                        (void *)&pcount, (void *)&bar_base};
+        auto t0 = std::chrono::steady_clock::now();
+        PCX_CUDA(cudaLaunchCooperativeKernel((const void *)wave_step_kernel, dim3(grid), dim3(threads), args, smem, s));
+        PCX_LAUNCHED();
+        bar_base += (unsigned)(1 + n.nlayers) * (unsigned)grid;
+        auto t1 = std::chrono::steady_clock::now();
+        PCX_CUDA(cudaStreamSynchronize(s));
+        auto t2 = std::chrono::steady_clock::now();
+        if (count > 0) {
+            rc = pool.run(g_pin.cdf[0], nullptr, g_pin.lab[0], count);
+            if (rc < 0) return rc;
+            total += (long long)count * n.nimg;
+        }
+        if (h_dbg) {
+            auto t3 = std::chrono::steady_clock::now();
+            host_us[3 * (size_t)step + 0] = std::chrono::duration<double, std::micro>(t1 - t0).count();
+            host_us[3 * (size_t)step + 1] = std::chrono::duration<double, std::micro>(t2 - t1).count();
+            host_us[3 * (size_t)step + 2] = std::chrono::duration<double, std::micro>(t3 - t2).count();
+        }
+        pfirst = first;
+        pcount = count;
+    }
+    cudaFree(d_start);
+    // the last step's symbols never pass through the network: one more DInput2 (pseudo_codec.py:159)
+    rc = pcx_dinput_step(dev_prev, n.layers[0].in, n.nimg, n.npart, n.G, n.h, n.W, n.pad, n.input_bias, n.nb, nsteps, n.d_order, n.h_start, s);
+    if (rc < 0) return rc;
+    PCX_CUDA(cudaStreamSynchronize(s));
+    if (h_dbg) {
+        FILE *f = fopen(trace_path, "w");
+        if (f) {
+            fprintf(f, "# step count launch_us sync_us code_us | device ns: dinput, layer 0..%d, gmm (block 0, globaltimer)\n", n.nlayers - 1);
+            for (int st = 0; st < nsteps; st++) {
+                Window w = wave_window(n.h_start, st, n.G, Hf, n.W);
+                fprintf(f, "%d %d %.1f %.1f %.1f |", st, w.count, host_us[3 * (size_t)st], host_us[3 * (size_t)st + 1], host_us[3 * (size_t)st + 2]);
+                for (int i = 1; i <= 2 + n.nlayers; i++)
+                    fprintf(f, " %lld", (long long)(h_dbg[(size_t)st * 32 + i] - h_dbg[(size_t)st * 32 + i - 1]));
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+        cudaFreeHost(h_dbg);
+    }
+    if (n_symbols) *n_symbols = total;
+    return PCX_OK;
+}
+
 int pcx_wave_decode(const pcx_wave_net *net, pcx_coder *const *coders, long long *n_symbols, void *stream)
 {
     int rc = wave_check(net);
@@ -1001,6 +1546,11 @@ int pcx_wave_decode(const pcx_wave_net *net, pcx_coder *const *coders, long long
     for (int i = 0; i < net->nimg; i++) PCX_REQUIRE(coders[i] != nullptr, "null coder for image %d", i);
     const pcx_wave_net &n = *net;
     cudaStream_t s = (cudaStream_t)stream;
+    if (g_wave_fused.load()) {
+        bool ok = n.nb == 3 && n.ng <= 3 && n.nstep <= 32;
+        for (int L = 0; L < n.nlayers; L++) ok = ok && n.layers[L].go == 3 && (n.layers[L].gi == 1 || n.layers[L].gi == 3);
+        if (ok) return wave_decode_fused(n, coders, n_symbols, s);
+    }
     const int Hf = n.h * n.npart, nsteps = pcx_wave_steps(net);
     const size_t max_rows = (size_t)n.nimg * (size_t)(Hf < n.W ? Hf : n.W) * n.G + 16;
     rc = ensure_pinned(max_rows, n.nstep);

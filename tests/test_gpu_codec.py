@@ -258,3 +258,31 @@ def test_one_shot_encoder_equals_stepwise_engine(codec, tmp_path):
         assert got == ref, "bitstreams of %s differ from the stepwise engine" % (key,)
     got = dec.ent.decode_batch(H // 128, W // 8, names)
     assert torch.equal(got, sym)
+
+
+def test_fused_step_decoder_equals_operator_sequence(codec, tmp_path):
+    """The decoder's wavefront step as ONE cooperative launch (halo taps interpolated on the fly, grid barriers between the
+    layers, mapped pinned CDF / symbol buffers) must decode the same symbols as the launch-per-operator sequence - for one
+    image and for a batch - from bitstreams written by the one-shot encoder."""
+    import torch
+    from pseudocylindrical_convolution_b200 import _lib
+    enc, dec, x, _ = codec
+    xs = torch.cat([x, torch.from_numpy(smooth_images(2, 3, H, W, seed=5)).to(x.device)]).contiguous()
+    sym = enc.symbols(xs)
+    names = [str(tmp_path / ("f%d.bin" % i)) for i in range(3)]
+    enc.ent.encode_batch(sym.clone(), names)
+    lib = _lib.load()
+    try:
+        for fused in (1, 0):
+            lib.pcx_wave_set_fused(fused)
+            n0 = lib.pcx_launch_count()
+            got = dec.ent.decode_batch(H // 128, W // 8, names)
+            launches = lib.pcx_launch_count() - n0
+            assert torch.equal(got, sym), "fused=%d: batch decode differs" % fused
+            dec.ent.start(names[1])
+            one = dec.ent(H // 128, W // 8)
+            assert torch.equal(one, sym[16:32]), "fused=%d: single-image decode differs" % fused
+            if fused:
+                assert launches <= 204 + 8, launches          # one launch per step (+ the final DInput2 / fill)
+    finally:
+        lib.pcx_wave_set_fused(1)
