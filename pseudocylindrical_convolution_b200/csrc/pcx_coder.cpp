@@ -25,33 +25,52 @@ constexpr uint64_t kQuarter = kHalf >> 1;            // second bit
 constexpr uint64_t kMinRange = (kFull >> 2) + 2;
 constexpr uint64_t kMaxTotal = kMinRange;            // min(2^64/2^32, MIN_RANGE)
 
+// MSB-first bit output: a 64-bit accumulator, whole bytes moved out when it fills (BitIoStream.cpp:52-72 emits the same bytes)
 struct BitSink {
     std::vector<unsigned char> bytes;
-    unsigned cur = 0;
-    int nbits = 0;
-    void put(unsigned bit)
+    uint64_t acc = 0;
+    int nbits = 0;                 // valid low bits of acc, < 8 between calls
+    void put_bits(uint32_t v, int n)            // n <= 32, the n low bits of v, most significant first
     {
-        cur = (cur << 1) | bit;
-        if (++nbits == 8) { bytes.push_back((unsigned char)cur); cur = 0; nbits = 0; }
+        if (n <= 0) return;
+        acc = (acc << n) | (uint64_t)(n == 32 ? v : (v & ((1u << n) - 1u)));
+        nbits += n;
+        while (nbits >= 8) {
+            nbits -= 8;
+            bytes.push_back((unsigned char)(acc >> nbits));
+        }
     }
-    void flush() { while (nbits != 0) put(0); }
+    void put(unsigned bit) { put_bits(bit, 1); }
+    void put_run(unsigned bit, uint64_t count)   // `count` copies of one bit
+    {
+        const uint32_t pat = bit ? 0xffffffffu : 0u;
+        while (count > 0) {
+            int n = count > 32 ? 32 : (int)count;
+            put_bits(pat, n);
+            count -= (uint64_t)n;
+        }
+    }
+    void flush() { if (nbits != 0) put_bits(0, 8 - nbits); }
 };
 
+// MSB-first bit input; past the end the stream reads as zeros (ArithmeticCoder.cpp:129-134)
 struct BitSource {
     std::vector<unsigned char> bytes;
     size_t pos = 0;
-    unsigned cur = 0;
-    int left = 0;
-    unsigned get()           // past the end the stream reads as zeros (ArithmeticCoder.cpp:129-134)
+    uint64_t acc = 0;
+    int left = 0;                  // valid low bits of acc
+    uint32_t get_bits(int n)       // n <= 32
     {
-        if (left == 0) {
-            if (pos >= bytes.size()) return 0;
-            cur = bytes[pos++];
-            left = 8;
+        if (n <= 0) return 0;
+        while (left < n) {
+            acc = (acc << 8) | (pos < bytes.size() ? bytes[pos] : 0u);
+            pos++;
+            left += 8;
         }
-        left--;
-        return (cur >> left) & 1u;
+        left -= n;
+        return (uint32_t)((acc >> left) & (n == 32 ? 0xffffffffull : ((1ull << n) - 1ull)));
     }
+    unsigned get() { return get_bits(1); }
 };
 
 }  // namespace
@@ -76,26 +95,36 @@ struct pcx_coder {
         const uint32_t lo = cum[sym], hi = cum[sym + 1];
         if (lo == hi) { pcx_set_error("coder: symbol %u has zero frequency", sym); return PCX_ECODER; }
         if (total > kMaxTotal) { pcx_set_error("coder: total %u too large", total); return PCX_ECODER; }
-        const uint64_t nl = low + (uint64_t)lo * range / total;
-        const uint64_t nh = low + (uint64_t)hi * range / total - 1;
+        // total is a power of two for every table the GMM stage emits (65536): the exact division becomes a shift
+        const bool p2 = (total & (total - 1)) == 0;
+        const int sh = __builtin_ctz(total);
+        const uint64_t nl = low + (p2 ? ((uint64_t)lo * range) >> sh : (uint64_t)lo * range / total);
+        const uint64_t nh = low + (p2 ? ((uint64_t)hi * range) >> sh : (uint64_t)hi * range / total) - 1;
         low = nl;
         high = nh;
-        while (((low ^ high) & kHalf) == 0) {            // top bits agree: shift one bit out
+        // The reference shifts one bit per iteration (ArithmeticCoder.cpp:51-68); here all the leading bits on which low and
+        // high agree leave in one go, then all the underflow bits (low = 01.., high = 10..) - the same bits in the same order.
+        const uint32_t diff = (uint32_t)(low ^ high);
+        const int n = diff == 0 ? 32 : __builtin_clz(diff);
+        if (n > 0) {
             if (ENC) {
-                unsigned bit = (unsigned)(low >> (kStateBits - 1));
+                const unsigned bit = (unsigned)(low >> (kStateBits - 1));
                 sink.put(bit);
-                for (; pending > 0; pending--) sink.put(bit ^ 1u);
+                if (pending > 0) { sink.put_run(bit ^ 1u, pending); pending = 0; }
+                if (n > 1) sink.put_bits((uint32_t)(low >> (kStateBits - n)), n - 1);
             } else {
-                code = ((code << 1) & kMask) | source.get();
+                code = n == 32 ? source.get_bits(32) : (((code << n) & kMask) | source.get_bits(n));
             }
-            low = (low << 1) & kMask;
-            high = ((high << 1) & kMask) | 1;
+            low = n == 32 ? 0 : (low << n) & kMask;
+            high = n == 32 ? kMask : (((high << n) & kMask) | ((1ull << n) - 1ull));
         }
-        while ((low & ~high & kQuarter) != 0) {          // low = 01.., high = 10..: underflow
-            if (ENC) pending++;
-            else code = (code & kHalf) | ((code << 1) & (kMask >> 1)) | source.get();
-            low = (low << 1) & (kMask >> 1);
-            high = ((high << 1) & (kMask >> 1)) | kHalf | 1;
+        const uint32_t under = (uint32_t)(low & ~high) << 1;   // bit 31 <- bit 30: run of positions with low = 1, high = 0
+        const int m = under == 0xffffffffu ? 31 : __builtin_clz(~under);
+        if (m > 0) {
+            if (ENC) pending += (uint64_t)m;
+            else code = (code & kHalf) | ((code << m) & (kMask >> 1)) | source.get_bits(m);
+            low = (low << m) & (kMask >> 1);
+            high = ((high << m) & (kMask >> 1)) | kHalf | ((1ull << m) - 1ull);
         }
         return PCX_OK;
     }
@@ -106,13 +135,16 @@ struct pcx_coder {
         const uint64_t range = high - low + 1;
         const uint64_t offset = code - low;
         const uint64_t value = ((offset + 1) * total - 1) / range;
-        if (value * range / total > offset || value >= total) { pcx_set_error("coder: decoder state inconsistent"); return PCX_ECODER; }
+        const bool p2 = (total & (total - 1)) == 0;
+        const int sh = __builtin_ctz(total);
+        if ((p2 ? (value * range) >> sh : value * range / total) > offset || value >= total) { pcx_set_error("coder: decoder state inconsistent"); return PCX_ECODER; }
         uint32_t a = 0, b = ncode;                        // highest symbol with cum[symbol] <= value
         while (b - a > 1) {
             uint32_t mid = (a + b) >> 1;
             if (cum[mid] > value) b = mid; else a = mid;
         }
-        if (offset < (uint64_t)cum[a] * range / total || (uint64_t)cum[a + 1] * range / total <= offset) {
+        if (offset < (p2 ? ((uint64_t)cum[a] * range) >> sh : (uint64_t)cum[a] * range / total) ||
+            (p2 ? ((uint64_t)cum[a + 1] * range) >> sh : (uint64_t)cum[a + 1] * range / total) <= offset) {
             pcx_set_error("coder: table does not bracket the code value (encoder/decoder CDF mismatch?)");
             return PCX_ECODER;
         }
@@ -205,7 +237,8 @@ static int begin_decode(pcx_coder *c)
     c->encoding = false;
     c->source.pos = 0;
     c->source.left = 0;
-    for (int i = 0; i < kStateBits; i++) c->code = (c->code << 1) | c->source.get();
+    c->source.acc = 0;
+    c->code = c->source.get_bits(kStateBits);
     return PCX_OK;
 }
 

@@ -355,17 +355,24 @@ __global__ void dextract_kernel(const float *__restrict__ in, float *__restrict_
 // (extension/entropy_gmm_table_cuda.cu:29-56, :83-105, :136-153) in one launch, one thread per symbol.
 // Expression shapes follow the reference's SASS: float v, FMUL s2*(v-mu), IEEE float division, erff,
 // DFMA(erf, .5, .5), DFMA(f, w, ps) rounded to float per component, FMUL total*ps, DADD .5, truncation.
-// w: mixture logits on entry, softmax weights on return; d: raw deltas on entry, clamped on return; c[0..nstep]: the table
-__device__ __forceinline__ void gmm_cdf_row(float *w, float *d, const float *mu, int ng, int nstep, float bias, float total,
+// w: mixture logits on entry, softmax weights on return; d: raw deltas on entry, clamped on return; c[0..nstep]: the table.
+// NGC / NSC > 0 fix the mixture size / number of steps at compile time (every loop unrolls, the arrays live in registers);
+// 0 takes the run-time value.  One source for both so that the expression shapes - and the bits - are the same.
+template <int NGC, int NSC>
+__device__ __forceinline__ void gmm_cdf_row(float *w, float *d, const float *mu, int ng_rt, int nstep_rt, float bias, float total,
                                             float beta, int form, float *c)
 {
+    const int ng = NGC > 0 ? NGC : ng_rt, nstep = NSC > 0 ? NSC : nstep_rt;
     float mval = -1e10f, psum = 0.f;
+#pragma unroll
     for (int i = 0; i < ng; i++)
         if (mval < w[i]) mval = w[i];
+#pragma unroll
     for (int i = 0; i < ng; i++) {
         w[i] = exp(w[i] - mval);
         psum += w[i];
     }
+#pragma unroll
     for (int i = 0; i < ng; i++) {
         w[i] = w[i] / psum;
         float t = d[i];
@@ -375,17 +382,20 @@ __device__ __forceinline__ void gmm_cdf_row(float *w, float *d, const float *mu,
     const float s2 = (float)(1. / sqrt(2.0));
     c[0] = 0.f;
     c[nstep] = (float)static_cast<int>(total);
+#pragma unroll
     for (int pt = 1; pt < nstep; pt++) {
         float v = pt - 1 - bias + 0.5;
         float ps = 0;
         if (form == 0) {
             // entropy_gmm_table_batch_forward_kernel (:146-150): the whole term stays in double, one rounding per component
+#pragma unroll
             for (int i = 0; i < ng; i++) {
                 ps = ps + w[i] * (0.5 + 0.5 * erf(s2 * (v - mu[i]) / d[i]));
             }
         } else {
             // entropy_gmm_table_forward_kernel (:69-72): f is stored to float first, then a float FFMA
             float f;
+#pragma unroll
             for (int i = 0; i < ng; i++) {
                 f = 0.5 + 0.5 * erf(s2 * (v - mu[i]) / d[i]);
                 ps = ps + w[i] * f;
@@ -396,13 +406,55 @@ __device__ __forceinline__ void gmm_cdf_row(float *w, float *d, const float *mu,
     // strict-monotonic fix-up (:83-105), on integer-valued floats as the reference does
     float fb = 0.f, mv = 0.f;
     int midx = 0;
+#pragma unroll
     for (int i = 0; i < nstep; i++) {
         if (c[i + 1] <= c[i]) fb += 1.f;
         c[i + 1] += fb;
         if (c[i + 1] - c[i] > mv) { mv = c[i + 1] - c[i]; midx = i; }
     }
-    if (fb > 0.f)
-        for (int i = midx; i < nstep; i++) c[i + 1] -= fb;
+    if (fb > 0.f) {
+#pragma unroll
+        for (int i = 0; i < nstep; i++)
+            if (i >= midx) c[i + 1] -= fb;
+    }
+}
+
+// Fast path of the table operator for the codec's shape (3 Gaussians, 8 symbols): a block owns 128 consecutive rows; the
+// three (n, 3) parameter arrays and the (n, 9) table pass through shared memory so that every global access is a coalesced
+// run, and the per-row state lives in registers.
+template <int FORM>
+__global__ void __launch_bounds__(128) gmm_table38_kernel(float *__restrict__ logit, float *__restrict__ delta,
+                                                          const float *__restrict__ mean, int n, float bias, float total,
+                                                          float beta, float *__restrict__ cdf_f, int *__restrict__ cdf_i)
+{
+    __shared__ float sp[3][128 * 3];
+    __shared__ float sc[128 * 9];
+    const int r0 = blockIdx.x * 128, rows = min(128, n - r0), t = threadIdx.x;
+    for (int i = t; i < rows * 3; i += 128) {
+        sp[0][i] = logit[(i64)r0 * 3 + i];
+        sp[1][i] = delta[(i64)r0 * 3 + i];
+        sp[2][i] = mean[(i64)r0 * 3 + i];
+    }
+    __syncthreads();
+    if (t < rows) {
+        float w[3], d[3], mu[3], c[9];
+#pragma unroll
+        for (int i = 0; i < 3; i++) { w[i] = sp[0][t * 3 + i]; d[i] = sp[1][t * 3 + i]; mu[i] = sp[2][t * 3 + i]; }
+        gmm_cdf_row<3, 8>(w, d, mu, 3, 8, bias, total, beta, FORM, c);
+#pragma unroll
+        for (int i = 0; i < 3; i++) { sp[0][t * 3 + i] = w[i]; sp[1][t * 3 + i] = d[i]; }
+#pragma unroll
+        for (int i = 0; i < 9; i++) sc[t * 9 + i] = c[i];
+    }
+    __syncthreads();
+    for (int i = t; i < rows * 3; i += 128) {          // in place, like the reference
+        logit[(i64)r0 * 3 + i] = sp[0][i];
+        delta[(i64)r0 * 3 + i] = sp[1][i];
+    }
+    for (int i = t; i < rows * 9; i += 128) {
+        if (cdf_f) cdf_f[(i64)r0 * 9 + i] = sc[i];
+        if (cdf_i) cdf_i[(i64)r0 * 9 + i] = (int)sc[i];
+    }
 }
 
 __global__ void gmm_table_kernel(float *__restrict__ logit, float *__restrict__ delta, const float *__restrict__ mean, int n,
@@ -418,7 +470,7 @@ __global__ void gmm_table_kernel(float *__restrict__ logit, float *__restrict__ 
         mu[i] = mean[(i64)r * ng + i];
     }
     float c[33];
-    gmm_cdf_row(w, d, mu, ng, nstep, bias, total, beta, form, c);
+    gmm_cdf_row<0, 0>(w, d, mu, ng, nstep, bias, total, beta, form, c);
     for (int i = 0; i < ng; i++) {
         logit[(i64)r * ng + i] = w[i];                  // in place, like the reference
         delta[(i64)r * ng + i] = d[i];
@@ -486,16 +538,19 @@ __global__ void gmm_ordered_kernel(const float *__restrict__ params, const float
     const int tw = hw % W, hp = hw / W, g = hp / h, th = hp % h;
     const int tc = s - tw - hp;
     const int Co = G * go;
-    float w[PCX_MAX_GAUSS], d[PCX_MAX_GAUSS], mu[PCX_MAX_GAUSS];
-    for (int i = 0; i < ng; i++) {
+    // ng == 3, nstep == 8 (checked by the launcher): the row state stays in registers
+    float w[3], d[3], mu[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
         const i64 cell = ((i64)tc * go + i) * h * W + (i64)th * W + tw;
         w[i] = params[(((i64)(0 * nimg + img) * npart + g) * Co) * h * W + cell];
         d[i] = params[(((i64)(1 * nimg + img) * npart + g) * Co) * h * W + cell];
         mu[i] = params[(((i64)(2 * nimg + img) * npart + g) * Co) * h * W + cell];
     }
-    float c[33];
-    gmm_cdf_row(w, d, mu, ng, nstep, bias, total, beta, 0, c);
-    for (int i = 0; i <= nstep; i++) cdf_i[t * (nstep + 1) + i] = (int)c[i];
+    float c[9];
+    gmm_cdf_row<3, 8>(w, d, mu, 3, 8, bias, total, beta, 0, c);
+#pragma unroll
+    for (int i = 0; i <= 8; i++) cdf_i[t * 9 + i] = (int)c[i];
     lab_i[t] = (int)data[((((i64)img * npart + g) * G + tc) * h + th) * W + tw];
 }
 
@@ -880,17 +935,19 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_step_kernel(const __grid_co
         const int hw = d.order[first + k];
         const int tw = hw % W, hp = hw / W, g = hp / h, th = hp % h;
         const int tc = step - tw - hp;
-        float w[PCX_MAX_GAUSS], dl[PCX_MAX_GAUSS], mu[PCX_MAX_GAUSS];
-        float pv[9];
+        float w[3], dl[3], mu[3];                          // ng == 3, nstep == 8 (checked by the launcher)
 #pragma unroll
-        for (int q = 0; q < 9; q++) {                     // 3 nets x 3 components, all loads in flight together
-            const int net = q / 3, i = q % 3;
-            pv[q] = i < d.ng ? __ldcg(last.out + ((((i64)(net * d.nimg + img) * d.npart + g) * h + th) * W + tw) * last.cp_out + tc * 3 + i) : 0.f;
+        for (int i = 0; i < 3; i++) {                     // 3 nets x 3 components, all loads in flight together
+            const float *pp = last.out + (((i64)img * d.npart + g) * h + th) * W * last.cp_out + (i64)tw * last.cp_out + tc * 3 + i;
+            const i64 net_stride = (i64)d.nimg * d.npart * h * W * last.cp_out;
+            w[i] = __ldcg(pp);
+            dl[i] = __ldcg(pp + net_stride);
+            mu[i] = __ldcg(pp + 2 * net_stride);
         }
-        for (int i = 0; i < d.ng && i < 3; i++) { w[i] = pv[i]; dl[i] = pv[3 + i]; mu[i] = pv[6 + i]; }
-        float c[33];
-        gmm_cdf_row(w, dl, mu, d.ng, d.nstep, d.gmm_bias, d.gmm_total, d.gmm_beta, 0, c);
-        for (int i = 0; i <= d.nstep; i++) d.cdf[(i64)t * (d.nstep + 1) + i] = (int)c[i];
+        float c[9];
+        gmm_cdf_row<3, 8>(w, dl, mu, 3, 8, d.gmm_bias, d.gmm_total, d.gmm_beta, 0, c);
+#pragma unroll
+        for (int i = 0; i <= 8; i++) d.cdf[(i64)t * 9 + i] = (int)c[i];
     }
     step_stamp(d, step, 2 + d.nlayers);
 }
@@ -1023,8 +1080,15 @@ int pcx_gmm_table(float *d_logit, float *d_delta, const float *d_mean, int n, in
     PCX_REQUIRE(nstep >= 2 && nstep <= 32, "nstep %d out of range", nstep);
     PCX_REQUIRE(form == 0 || form == 1, "form %d", form);
     if (n <= 0) return PCX_OK;                                             // tn > 0 (:163)
-    gmm_table_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(d_logit, d_delta, d_mean, n, ng, nstep, bias, total,
-                                                                         beta, form, d_cdf_f, d_cdf_i);
+    if (ng == 3 && nstep == 8) {
+        if (form == 0)
+            gmm_table38_kernel<0><<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(d_logit, d_delta, d_mean, n, bias, total, beta, d_cdf_f, d_cdf_i);
+        else
+            gmm_table38_kernel<1><<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(d_logit, d_delta, d_mean, n, bias, total, beta, d_cdf_f, d_cdf_i);
+    } else {
+        gmm_table_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(d_logit, d_delta, d_mean, n, ng, nstep, bias, total,
+                                                                             beta, form, d_cdf_f, d_cdf_i);
+    }
     PCX_LAUNCHED();
     return PCX_OK;
 }
@@ -1250,6 +1314,7 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
     for (int i = 0; i < net->nimg; i++) PCX_REQUIRE(coders[i] != nullptr, "null coder for image %d", i);
     const pcx_wave_net &n = *net;
     PCX_REQUIRE(n.d_lab && n.d_steptab && n.cdf_rows > 0, "one-shot encoding needs d_lab, d_steptab and cdf_rows");
+    PCX_REQUIRE(n.ng == 3 && n.nstep == 8, "the one-shot encoder is built for 3 Gaussians / 8 symbols (got %d / %d)", n.ng, n.nstep);
     cudaStream_t s = (cudaStream_t)stream;
     const int Hf = n.h * n.npart, nsteps = pcx_wave_steps(net), nrep = n.nb * n.nimg;
     Bands bands;
@@ -1547,7 +1612,7 @@ int pcx_wave_decode(const pcx_wave_net *net, pcx_coder *const *coders, long long
     const pcx_wave_net &n = *net;
     cudaStream_t s = (cudaStream_t)stream;
     if (g_wave_fused.load()) {
-        bool ok = n.nb == 3 && n.ng <= 3 && n.nstep <= 32;
+        bool ok = n.nb == 3 && n.ng == 3 && n.nstep == 8;
         for (int L = 0; L < n.nlayers; L++) ok = ok && n.layers[L].go == 3 && (n.layers[L].gi == 1 || n.layers[L].gi == 3);
         if (ok) return wave_decode_fused(n, coders, n_symbols, s);
     }

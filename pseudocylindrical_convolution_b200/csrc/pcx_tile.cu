@@ -251,6 +251,112 @@ __global__ void __launch_bounds__(512) pad_rows_kernel(const float *__restrict__
     }
 }
 
+// Same operator without the shared-memory row pipeline: one WARP per output row, lanes stride over the row in vectors of VEC
+// columns, everything read straight from global memory (a padded row is its source row shifted by `pad` columns, so the scalar
+// loads of a warp are contiguous; the wrap columns and the 2-tap halo rows hit L1/L2).  No block-wide synchronisation at all:
+// this is what lets the copy stream at HBM speed - the staged version above spends two barriers per 8 KB row.
+template <bool CAUSAL>
+__device__ __forceinline__ float pad_value(const float *__restrict__ src, int hr, int xo, int wl, int wsrc, int W, int pad,
+                                           const int *__restrict__ hcol, const float *__restrict__ htw)
+{
+    int x = xo - pad;                        // column in the unpadded tile
+    if (x < 0) x = CAUSAL ? -1 : x + wl;     // left pad: last `pad` valid columns (0 when causal)
+    else if (x >= wl) { x -= wl; if (x >= pad) x = -1; }   // right pad: first `pad` valid columns
+    if (x < 0 || src == nullptr) return 0.f;
+    if (hr < 0) return __ldg(src + x);
+    const i64 e = (i64)hr * W + x;
+    const int q = hcol[e];
+    const float a = (CAUSAL && q < 0) ? 0.f : __ldg(src + (q < 0 ? q + wsrc : q));
+    const int q1 = q + 1 >= wsrc ? q + 1 - wsrc : q + 1;
+    return lerp2_ref(a, __ldg(src + q1), htw[e]);
+}
+
+// The bulk of a row is written with 16-byte-aligned 128-bit stores whatever the pitch (2050-float rows of pad = 1 start on
+// 8-byte boundaries): up to three leading and trailing columns are peeled off as scalar stores.
+template <bool CAUSAL>
+__global__ void __launch_bounds__(256) pad_direct_kernel(const float *__restrict__ in, float *__restrict__ out, Bands bands,
+                                                         const int *__restrict__ hband, const int *__restrict__ hrow,
+                                                         const int *__restrict__ hcol, const float *__restrict__ htw,
+                                                         i64 nrows, int C, int h, int W, int pad, int out_pitch)
+{
+    const int lane = threadIdx.x & 31;
+    const i64 warp0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    const int npart = bands.npart, out_h = h + 2 * pad;
+    for (i64 R = warp0; R < nrows; R += nwarps) {
+        const i64 plane = R / out_h;
+        const int y = (int)(R - plane * out_h);
+        const int c = (int)(plane % C);
+        const i64 tile = plane / C;
+        const int g = (int)(tile % npart);
+        const int wl = bands.wl[g];
+        const float *src = nullptr;
+        int hr = -1, wsrc = wl;
+        if (y >= pad && y < pad + h) {
+            src = in + (plane * h + (y - pad)) * (i64)W;
+        } else {
+            const int s = y < pad ? 0 : 1, r = y < pad ? y : y - pad - h;
+            hr = (g * 2 + s) * pad + r;
+            const int pg = hband[hr];
+            if (pg >= 0) {
+                src = in + ((((tile / npart) * npart + pg) * C + c) * h + hrow[hr]) * (i64)W;
+                wsrc = bands.wl[pg];
+            }
+        }
+        float *dst = out + R * (i64)out_pitch;
+        const int lead = (int)(((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15) >> 2);       // floats before alignment
+        const int nv = (out_pitch - lead) >> 2;                                                  // aligned vectors
+        if (lane < lead) dst[lane] = pad_value<CAUSAL>(src, hr, lane, wl, wsrc, W, pad, hcol, htw);
+        const int tail0 = lead + nv * 4;
+        if (tail0 + lane < out_pitch && lane < 4) dst[tail0 + lane] = pad_value<CAUSAL>(src, hr, tail0 + lane, wl, wsrc, W, pad, hcol, htw);
+        if (src != nullptr && hr < 0) {
+            // interior row: vectors [ivB0, ivB1) are plain shifted copies, [ivB1, ivC) hold the right wrap, the rest is zero
+            const int ivB0 = lead >= pad ? 0 : (pad - lead + 3) >> 2;
+            int ivB1 = (wl + pad - lead) >> 2;                     // first vector with x0 + 3 - pad >= wl
+            ivB1 = ivB1 < ivB0 ? ivB0 : (ivB1 > nv ? nv : ivB1);
+            int ivC = (wl + 2 * pad - lead + 3) >> 2;              // first vector that lies wholly beyond the wrap columns
+            ivC = ivC < ivB1 ? ivB1 : (ivC > nv ? nv : ivC);
+            const float *sp = src + lead - pad;
+            int iv = ivB0 + lane;
+            for (; iv + 96 < ivB1; iv += 128) {                    // four vectors per lane, sixteen loads in flight
+                float v[4][4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) v[u][j] = __ldg(sp + (iv + 32 * u) * 4 + j);
+#pragma unroll
+                for (int u = 0; u < 4; u++) st_cs_f4(dst + lead + (iv + 32 * u) * 4, make_float4(v[u][0], v[u][1], v[u][2], v[u][3]));
+            }
+            for (; iv < ivB1; iv += 32) {
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] = __ldg(sp + iv * 4 + j);
+                st_cs_f4(dst + lead + iv * 4, make_float4(v[0], v[1], v[2], v[3]));
+            }
+            for (iv = lane; iv < ivB0; iv += 32) {                  // left wrap
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] = pad_value<CAUSAL>(src, hr, lead + iv * 4 + j, wl, wsrc, W, pad, hcol, htw);
+                st_cs_f4(dst + lead + iv * 4, make_float4(v[0], v[1], v[2], v[3]));
+            }
+            for (iv = ivB1 + lane; iv < ivC; iv += 32) {            // last valid columns + right wrap
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] = pad_value<CAUSAL>(src, hr, lead + iv * 4 + j, wl, wsrc, W, pad, hcol, htw);
+                st_cs_f4(dst + lead + iv * 4, make_float4(v[0], v[1], v[2], v[3]));
+            }
+            for (iv = ivC + lane; iv < nv; iv += 32) st_cs_f4(dst + lead + iv * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+        } else {
+            for (int iv = lane; iv < nv; iv += 32) {                // halo rows (2-tap gathers) and pole rows (zeros)
+                const int x0 = lead + iv * 4;
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] = pad_value<CAUSAL>(src, hr, x0 + j, wl, wsrc, W, pad, hcol, htw);
+                st_cs_f4(dst + x0, make_float4(v[0], v[1], v[2], v[3]));
+            }
+        }
+    }
+}
+
 // In-place halo refresh of a padded, pitched buffer: only halo rows and wrap columns are touched.
 // Same values as pad_rows_kernel<*, false>.  One thread per written cell.
 __global__ void halo_fill_kernel(float *__restrict__ buf, Bands bands, const int *__restrict__ hband,
@@ -340,6 +446,44 @@ __global__ void dtow_kernel(const float *__restrict__ in, float *__restrict__ ou
     }
 }
 
+// stride-2 fast paths: 128-bit stores, 64/128-bit loads, 32-bit index arithmetic.
+// d2w: out (N, C/4, 2H, 2W); four output columns come from two consecutive columns of two input channels.
+__global__ void __launch_bounds__(256) dtow2_d2w_kernel(const float *__restrict__ in, float *__restrict__ out, unsigned nvec, int C,
+                                                        int H, int W)
+{
+    const unsigned Co = C / 4, Ho = 2 * H, WV = (2 * W) / 4;
+    const i64 chs = (i64)H * W;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
+        const unsigned row = i / WV, xv = i - row * WV;
+        const unsigned py = row % Ho, pcn = row / Ho;
+        const unsigned pc = pcn % Co, n = pcn / Co;
+        const float *src = in + (((i64)n * C + pc * 4 + (py & 1) * 2) * H + (py >> 1)) * W + xv * 2;
+        const float2 a = __ldcs(reinterpret_cast<const float2 *>(src));
+        const float2 b = __ldcs(reinterpret_cast<const float2 *>(src + chs));
+        st_cs_f4(out + (i64)i * 4, make_float4(a.x, b.x, a.y, b.y));
+    }
+}
+// w2d: out (N, 4C, H/2, W/2); eight consecutive input columns of one row feed four columns of two output channels.
+__global__ void __launch_bounds__(256) dtow2_w2d_kernel(const float *__restrict__ in, float *__restrict__ out, unsigned nvec, int C,
+                                                        int H, int W)
+{
+    const unsigned Ho = H / 2, Wo = W / 2, WV = Wo / 4;
+    const i64 ochs = (i64)Ho * Wo;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
+        unsigned t = i / WV;
+        const unsigned xv = i - t * WV;
+        const unsigned r = t & 1; t >>= 1;
+        const unsigned oy = t % Ho; t /= Ho;
+        const unsigned c = t % (unsigned)C, n = t / (unsigned)C;
+        const float *src = in + (((i64)n * C + c) * H + oy * 2 + r) * W + xv * 8;
+        const float4 a = __ldcs(reinterpret_cast<const float4 *>(src));
+        const float4 b = __ldcs(reinterpret_cast<const float4 *>(src + 4));
+        float *dst = out + (((i64)n * C * 4 + c * 4 + r * 2) * Ho + oy) * Wo + xv * 4;
+        st_cs_f4(dst, make_float4(a.x, a.z, b.x, b.z));
+        st_cs_f4(dst + ochs, make_float4(a.y, a.w, b.y, b.w));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ launch helpers
 struct StripPlan { int rows_per_cta, strips; };
 
@@ -422,27 +566,13 @@ int launch_pad(const float *d_in, float *d_out, int N, int C, int h, int W, int 
     PCX_REQUIRE(W <= 8192, "W=%d exceeds the 8192-column limit of the row pipeline", W);
     for (int i = 0; i < npart; i++) PCX_REQUIRE(wl[i] >= 2 * pad && wl[i] <= W, "band %d width %d outside [%d,%d]", i, wl[i], 2 * pad, W);
     i64 planes = (i64)N * npart * C;
-    StripPlan sp = plan_strips(planes, h + 2 * pad);
-    PCX_REQUIRE(planes * sp.strips < (1ll << 31), "grid too large");
-    bool bulk = (W % 4 == 0) && aligned16(d_in);
-    int vec = (out_pitch % 4 == 0 && aligned16(d_out)) ? 4 : ((out_pitch % 2 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 7) == 0) ? 2 : 1);
-    int threads = ((out_pitch + vec - 1) / vec + 31) / 32 * 32;
-    if (threads > 512) threads = 512;
-    if (threads < 64) threads = 64;
-    size_t smem = stager_smem(W);
-    dim3 grid((unsigned)(planes * sp.strips));
     cudaStream_t s = (cudaStream_t)stream;
-#define PCX_PAD(V)                                                                                              \
-    do {                                                                                                        \
-        int rc = allow_smem(pad_rows_kernel<V, CAUSAL>, smem);                                                  \
-        if (rc) return rc;                                                                                      \
-        pad_rows_kernel<V, CAUSAL><<<grid, threads, smem, s>>>(d_in, d_out, b, d_band, d_row, d_col, d_tw, C, h, W, pad, \
-                                                               out_pitch, sp.rows_per_cta, sp.strips, bulk);     \
-    } while (0)
-    if (vec == 4) PCX_PAD(4);
-    else if (vec == 2) PCX_PAD(2);
-    else PCX_PAD(1);
-#undef PCX_PAD
+    // one warp per output row, 8 rows per CTA, a few CTAs per SM (grid-stride over the rows)
+    const i64 nrows = planes * (h + 2 * pad);
+    i64 want = (nrows + 7) / 8;
+    const i64 cap = (i64)pcx_sm_count() * 8;
+    const int blocks = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    pad_direct_kernel<CAUSAL><<<blocks, 256, 0, s>>>(d_in, d_out, b, d_band, d_row, d_col, d_tw, nrows, C, h, W, pad, out_pitch);
     PCX_LAUNCHED();
     return PCX_OK;
 }
@@ -510,6 +640,17 @@ int pcx_dtow(const float *d_in, float *d_out, int N, int C, int H, int W, int st
     if (d2w) PCX_REQUIRE(C % (stride * stride) == 0, "channels %d not divisible by stride^2", C);
     else PCX_REQUIRE(H % stride == 0 && W % stride == 0, "H/W not divisible by stride");
     i64 total = (i64)N * C * H * W;
+    const bool al = ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
+    if (stride == 2 && al && total / 4 < (1ll << 31) && (d2w ? W % 2 == 0 : W % 8 == 0)) {
+        // d2w: one thread per 4 output columns; w2d: one thread per 8 input columns
+        const i64 nvec = d2w ? total / 4 : total / 8;
+        i64 want = (nvec + 255) / 256;
+        int blocks = (int)(want < (i64)pcx_sm_count() * 16 ? (want < 1 ? 1 : want) : (i64)pcx_sm_count() * 16);
+        if (d2w) dtow2_d2w_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, (unsigned)nvec, C, H, W);
+        else dtow2_w2d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, (unsigned)nvec, C, H, W);
+        PCX_LAUNCHED();
+        return PCX_OK;
+    }
     i64 want = (total + 255) / 256;
     int blocks = (int)(want < (i64)pcx_sm_count() * 32 ? want : (i64)pcx_sm_count() * 32);
     dtow_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, total, C, H, W, stride, d2w != 0);

@@ -217,6 +217,46 @@ def test_coder_bytes_identical_to_reference(ref_coder, tmp_path):
     assert (r2.decodes(t, 8, n).numpy()[:n].astype(np.int32) == sym).all()
 
 
+def test_coder_multibit_renormalisation_matches_reference(ref_coder, tmp_path):
+    """The product coder shifts all agreeing / underflow bits in one go and divides by power-of-two totals with a shift;
+    the reference shifts bit by bit and divides.  Width-1 symbols (16-bit bursts), long underflow runs (symbols straddling
+    the midpoint) and non-power-of-two totals must give the same bytes, and both decoders must agree."""
+    import torch
+    from pseudocylindrical_convolution_b200 import coder as mycoder
+    if ref_coder is None:
+        pytest.skip("oracle/_ref/coder_ref.so not built")
+    rng = np.random.default_rng(11)
+    n = 30000
+    cum = np.zeros((n, 9), np.int64)
+    sym = np.zeros(n, np.int32)
+    for i in range(n):
+        kind = i % 4
+        total = 65536 if kind != 3 else int(rng.integers(9, 70000))
+        if kind == 0:                       # one dominant symbol, seven of width 1; code the rare ones often
+            big = int(rng.integers(0, 8))
+            w = np.ones(8, np.int64); w[big] = total - 7
+            sym[i] = big if rng.random() < 0.5 else int(rng.integers(0, 8))
+        elif kind == 1:                     # two halves meeting at the midpoint: underflow runs
+            w = np.ones(8, np.int64); w[3] = total // 2 - 3; w[4] = total - 7 - w[3] + 1
+            sym[i] = int(rng.choice([3, 4]))
+        else:
+            w = rng.integers(1, max(2, total // 8), size=8).astype(np.int64)
+            w[-1] += max(0, total - w.sum())
+            sym[i] = int(rng.integers(0, 8))
+        c = np.concatenate([[0], np.cumsum(w)])
+        cum[i] = c
+    cum = cum.astype(np.int32)
+    t, s_ = torch.from_numpy(cum), torch.from_numpy(sym)
+    mine = mycoder.coder(str(tmp_path / "m.bin"))
+    mine.start_encoder(); mine.encodes(t, 8, s_, n); mine.end_encoder()
+    ref = ref_coder.coder(str(tmp_path / "r.bin"))
+    ref.start_encoder(); ref.encodes(t, 8, s_, n); ref.end_encoder()
+    assert open(tmp_path / "m.bin", "rb").read() == open(tmp_path / "r.bin", "rb").read()
+    d = mycoder.coder(str(tmp_path / "r.bin"))
+    d.start_decoder()
+    assert (d.decodes(t, 8, n).numpy().astype(np.int32) == sym).all()
+
+
 def test_coder_errors_are_loud(tmp_path):
     import torch
     from pseudocylindrical_convolution_b200 import coder as mycoder
