@@ -707,7 +707,7 @@ __device__ __forceinline__ void reg_fence_v4(float4 &a, float4 &b)
 // The block's share of a step: one (net image pn, plane) pair and a run of that plane's cells.  All cells of a plane carry
 // the same channel group tc = step - plane, so the three output rows of (net, tc) are the only weights the block needs:
 // they are staged in shared memory with cp.async one layer AHEAD (weights do not depend on the grid barrier).
-struct StepChunk { int pn, plane, cell0, ncell; };
+struct StepChunk { int net, plane, cell0, ncell; };   // cells cell0 .. cell0+ncell of the plane's (image, cell) list
 
 constexpr int STEP_THREADS = 256;
 
@@ -719,7 +719,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// rows of outputs tc*3 .. tc*3+2 of net b, channel groups < gmax: smem[og * wstride + r], r = ci * 25 + tap
+// rows of outputs tc*3 .. tc*3+2 of net b, channel groups < gmax, interleaved as smem[(ci * 25 + tap) * 4 + og] so that one
+// 128-bit shared load fetches the three weights of a (channel, tap); bias and PReLU slope sit behind them at 4 * wstride.
 __device__ __forceinline__ void step_stage_weights(const StepNet &d, const StepLayer &l, int b, int tc, float *smem, int wstride)
 {
     const int Ci = d.G * l.gi, Co = d.G * 3;
@@ -728,11 +729,10 @@ __device__ __forceinline__ void step_stage_weights(const StepNet &d, const StepL
     const int nw = gmax * l.gi * 25;
     for (int i = threadIdx.x; i < nw * 3; i += blockDim.x) {
         const int og = i / nw, r = i % nw;
-        cp_async4(smem + og * wstride + r, l.weight + (((i64)b * Co + tc * 3 + og) * Ci) * 25 + r);
+        cp_async4(smem + r * 4 + og, l.weight + (((i64)b * Co + tc * 3 + og) * Ci) * 25 + r);
     }
-    // bias and PReLU slope of the three outputs behind the weight rows
-    if (threadIdx.x < 3) cp_async4(smem + 3 * wstride + threadIdx.x, l.bias + b * Co + tc * 3 + threadIdx.x);
-    else if (threadIdx.x < 6 && l.act != nullptr) cp_async4(smem + 3 * wstride + threadIdx.x, l.act + b * Co + tc * 3 + threadIdx.x - 3);
+    if (threadIdx.x < 3) cp_async4(smem + 4 * wstride + threadIdx.x, l.bias + b * Co + tc * 3 + threadIdx.x);
+    else if (threadIdx.x < 6 && l.act != nullptr) cp_async4(smem + 4 * wstride + threadIdx.x, l.act + b * Co + tc * 3 + threadIdx.x - 3);
 }
 
 // One warp per cell.  Lane = filter tap (kh, kw) (25 live lanes); it runs the GI chains of its tap - the reference's virtual
@@ -748,17 +748,19 @@ __device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLaye
     const int cp = l.cp_in;
     constexpr int NQ = 2 * GI;                                  // float4 per batch of 8 channel groups
     const int c6 = l.constrain == 6 ? 1 : 0;
-    const int pn = ch.pn, tc = step - ch.plane;
-    const int first = start[ch.plane] + ch.cell0;
+    const int tc = step - ch.plane;
+    const int first = start[ch.plane], pcells = start[ch.plane + 1] - start[ch.plane];
     const bool live = lane < 25;
     const int kw = lane % 5, kh = (lane / 5) % 5;
     int nk_tap = live ? tc + 4 - kh - kw + c6 : 0;
     nk_tap = nk_tap > G ? G : (nk_tap < 0 ? 0 : nk_tap);
     int gmax = tc + 4 + c6;                                     // longest chain of the block (tap 0,0)
     gmax = gmax > G ? G : gmax;
-    const float *wl_ = ws + kh * 5 + kw;
+    const float4 *wl_ = reinterpret_cast<const float4 *>(ws) + kh * 5 + kw;
     for (int k = warp; k < ch.ncell; k += nwarp) {
-        const int hw = d.order[first + k];
+        const int e = ch.cell0 + k, img = e / pcells;
+        const int pn = ch.net * d.nimg + img;
+        const int hw = d.order[first + e - img * pcells];
         const int tw = hw % W, hp = hw / W, g = hp / h, th = hp % h;
         StepTap tp;
         tp.pa = tp.pb = l.in;
@@ -786,23 +788,27 @@ __device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLaye
                 reg_fence_v4(xa[q], xa[q + 1]);
                 reg_fence_v4(xb[q], xb[q + 1]);
             }
-            float va[8 * GI], vb[8 * GI];
+            float va[8 * GI];
 #pragma unroll
-            for (int q = 0; q < NQ; q++) {
-                va[4 * q] = xa[q].x; va[4 * q + 1] = xa[q].y; va[4 * q + 2] = xa[q].z; va[4 * q + 3] = xa[q].w;
-                vb[4 * q] = xb[q].x; vb[4 * q + 1] = xb[q].y; vb[4 * q + 2] = xb[q].z; vb[4 * q + 3] = xb[q].w;
+            for (int q = 0; q < NQ; q++) { va[4 * q] = xa[q].x; va[4 * q + 1] = xa[q].y; va[4 * q + 2] = xa[q].z; va[4 * q + 3] = xa[q].w; }
+            if (tp.mode != 0) {                                  // halo / wrap-of-halo tap: causal 2-tap interpolation (+0 when mode 2)
+                float vb[8 * GI];
+#pragma unroll
+                for (int q = 0; q < NQ; q++) { vb[4 * q] = xb[q].x; vb[4 * q + 1] = xb[q].y; vb[4 * q + 2] = xb[q].z; vb[4 * q + 3] = xb[q].w; }
+#pragma unroll
+                for (int e = 0; e < 8 * GI; e++) va[e] = lerp2_ref(va[e], vb[e], tp.t);
             }
 #pragma unroll
             for (int u = 0; u < 8; u++) {
-                const bool act_k = c0 + u < nk;
-                const float *w = wl_ + (act_k ? (c0 + u) * GI * 25 : 0);
+                if (c0 + u < nk) {
 #pragma unroll
-                for (int m = 0; m < GI; m++) {
-                    const float a = va[u * GI + m];             // +0 when mode == 2 (load predicated off)
-                    const float v = tp.mode == 0 ? a : lerp2_ref(a, vb[u * GI + m], tp.t);
-                    acc[m][0] = act_k ? __fmaf_rn(v, w[m * 25], acc[m][0]) : acc[m][0];
-                    acc[m][1] = act_k ? __fmaf_rn(v, w[m * 25 + wstride], acc[m][1]) : acc[m][1];
-                    acc[m][2] = act_k ? __fmaf_rn(v, w[m * 25 + 2 * wstride], acc[m][2]) : acc[m][2];
+                    for (int m = 0; m < GI; m++) {
+                        const float4 w = wl_[((c0 + u) * GI + m) * 25];
+                        const float v = va[u * GI + m];
+                        acc[m][0] = __fmaf_rn(v, w.x, acc[m][0]);
+                        acc[m][1] = __fmaf_rn(v, w.y, acc[m][1]);
+                        acc[m][2] = __fmaf_rn(v, w.z, acc[m][2]);
+                    }
                 }
             }
         }
@@ -837,8 +843,8 @@ __device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLaye
         if (lane == 0) {
 #pragma unroll
             for (int og = 0; og < 3; og++) {
-                float v = __fadd_rn(sum[og], ws[3 * wstride + og]);
-                if (l.act != nullptr && v < 0.f) v = __fmul_rn(v, ws[3 * wstride + 3 + og]);
+                float v = __fadd_rn(sum[og], ws[4 * wstride + og]);
+                if (l.act != nullptr && v < 0.f) v = __fmul_rn(v, ws[4 * wstride + 3 + og]);
                 if (l.add != nullptr) v = __fadd_rn(v, addv[og]);
                 l.out[o + og] = v;
             }
@@ -846,20 +852,21 @@ __device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLaye
     }
 }
 
-// run `id` of the step: every (net image, plane) pair of the window is cut into runs of at most S cells
-__device__ __forceinline__ StepChunk step_chunk_of(const int *__restrict__ start, int id, int p0, int np, int S, int nrep)
+// run `id` of the step: for every (net, plane) pair of the window the cells of ALL images (they share the weights) form one
+// list of nimg * cells entries, cut into runs of at most S
+__device__ __forceinline__ StepChunk step_chunk_of(const int *__restrict__ start, int id, int p0, int np, int S, int nb, int nimg)
 {
     StepChunk c = {0, p0, 0, 0};
     for (int q = p0; q < p0 + np; q++) {
-        const int cells = start[q + 1] - start[q];
+        const int cells = (start[q + 1] - start[q]) * nimg;
         const int nrun = (cells + S - 1) / S;
-        if (id < nrun * nrep) {
+        if (id < nrun * nb) {
             const int run = id % nrun;
-            c.pn = id / nrun; c.plane = q; c.cell0 = run * S;
+            c.net = id / nrun; c.plane = q; c.cell0 = run * S;
             c.ncell = cells - run * S < S ? cells - run * S : S;
             return c;
         }
-        id -= nrun * nrep;
+        id -= nrun * nb;
     }
     return c;
 }
@@ -871,7 +878,7 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_step_kernel(const __grid_co
                                                                  int step, int p0, int np, int S, int nchunk, int pfirst, int pcount,
                                                                  unsigned bar_base)
 {
-    extern __shared__ float step_ws[];                // 2 buffers of 3 * wstride weights + 8 (bias, slope)
+    extern __shared__ __align__(16) float step_ws[];  // 2 buffers of 4 * wstride weights + 8 (bias, slope)
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     const int h = d.h, W = d.W, pad = d.pad, G = d.G, nrep = d.nb * d.nimg;
     const int wstride = G * 3 * 25;
@@ -881,8 +888,8 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_step_kernel(const __grid_co
     const int nmy = blockIdx.x < nchunk ? (nchunk - 1 - blockIdx.x) / gridDim.x + 1 : 0;      // my runs per layer
     const int nitems = nmy * d.nlayers;
     if (nitems > 0) {
-        const StepChunk c0 = step_chunk_of(start, blockIdx.x, p0, np, S, nrep);
-        step_stage_weights(d, d.L[0], c0.pn / d.nimg, step - c0.plane, step_ws, wstride);
+        const StepChunk c0 = step_chunk_of(start, blockIdx.x, p0, np, S, d.nb, d.nimg);
+        step_stage_weights(d, d.L[0], c0.net, step - c0.plane, step_ws, wstride);
     }
     cp_async_commit();
     // ---- DInput2: the symbols decoded at step - 1 enter the padded input (3 replicas)
@@ -909,17 +916,17 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_step_kernel(const __grid_co
     int it = 0;
     for (int L = 0; L < d.nlayers; L++) {
         for (int ci = 0; ci < nmy; ci++, it++) {
-            const StepChunk ch = step_chunk_of(start, blockIdx.x + ci * gridDim.x, p0, np, S, nrep);
+            const StepChunk ch = step_chunk_of(start, blockIdx.x + ci * gridDim.x, p0, np, S, d.nb, d.nimg);
             if (ci > 0) __syncthreads();               // every warp is done with item it-1: its buffer may be refilled
             if (it + 1 < nitems) {
                 const int nci = ci + 1 < nmy ? ci + 1 : 0, nL = ci + 1 < nmy ? L : L + 1;
-                const StepChunk nc = step_chunk_of(start, blockIdx.x + nci * gridDim.x, p0, np, S, nrep);
-                step_stage_weights(d, d.L[nL], nc.pn / d.nimg, step - nc.plane, step_ws + ((it + 1) & 1) * (3 * wstride + 8), wstride);
+                const StepChunk nc = step_chunk_of(start, blockIdx.x + nci * gridDim.x, p0, np, S, d.nb, d.nimg);
+                step_stage_weights(d, d.L[nL], nc.net, step - nc.plane, step_ws + ((it + 1) & 1) * (4 * wstride + 8), wstride);
             }
             cp_async_commit();
             cp_async_wait<1>();                        // this item's rows have landed; the next item's may still be in flight
             __syncthreads();
-            const float *ws = step_ws + (it & 1) * (3 * wstride + 8);
+            const float *ws = step_ws + (it & 1) * (4 * wstride + 8);
             if (d.L[L].gi == 1) step_conv_phase<1>(d, d.L[L], step, ch, start, ws, wstride);
             else step_conv_phase<3>(d, d.L[L], step, ch, start, ws, wstride);
         }
@@ -1518,7 +1525,7 @@ static int wave_decode_fused(const pcx_wave_net &n, pcx_coder *const *coders, lo
     PCX_CUDA(cudaMemsetAsync(n.layers[0].in, 0, sizeof(float) * (size_t)nrep * n.npart * n.G * (n.h + 2 * n.pad) * (n.W + 2 * n.pad), s));
 
     const int threads = STEP_THREADS;
-    const size_t smem = sizeof(float) * 2 * (3 * (size_t)n.G * 3 * 25 + 8);
+    const size_t smem = sizeof(float) * 2 * (4 * (size_t)n.G * 3 * 25 + 8);
     PCX_CUDA(cudaFuncSetAttribute(wave_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     PCX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wave_step_kernel, threads, smem));
@@ -1545,13 +1552,14 @@ static int wave_decode_fused(const pcx_wave_net &n, pcx_coder *const *coders, lo
         const int wpb = threads / 32;
         int maxcells = 1;
         for (int q = p0; q < p1; q++) maxcells = n.h_start[q + 1] - n.h_start[q] > maxcells ? n.h_start[q + 1] - n.h_start[q] : maxcells;
+        maxcells *= n.nimg;
         int S = wpb, nchunk = 0;
         long best = -1;
         for (int cand = wpb; cand < maxcells + wpb; cand += wpb) {
             int chunks = 0;
-            for (int q = p0; q < p1; q++) chunks += nrep * ceil_div(n.h_start[q + 1] - n.h_start[q], cand);
+            for (int q = p0; q < p1; q++) chunks += n.nb * ceil_div((i64)(n.h_start[q + 1] - n.h_start[q]) * n.nimg, cand);
             const long cost = (long)ceil_div(chunks, max_grid) * (cand / wpb);
-            if (best < 0 || cost < best) { best = cost; S = cand; nchunk = chunks; }
+            if (best < 0 || cost <= best) { best = cost; S = cand; nchunk = chunks; }      // ties: the longer run (fewer weight stagings)
         }
         int grid = nchunk < max_grid ? nchunk : max_grid;
         if (grid < 1) grid = 1;
