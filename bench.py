@@ -189,6 +189,46 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def time_codec(dev, local, rank, sharding):
+    """Full encode / decode wall-clock (host included) of 512x1024 images, per GPU; whole-job MP/s = all ranks / slowest rank."""
+    import tempfile
+    import torch
+    from pseudocylindrical_convolution_b200 import pseudo_codec as pc
+    from pseudocylindrical_convolution_b200.random_init import synthesize_checkpoints
+    Hc, Wc, vd = 512, 1024, 56
+    d = tempfile.mkdtemp(prefix="pcx_bench_r%d_" % rank)
+    p_enc, p_dec, p_ent = synthesize_checkpoints(d, "4_56", vd, local, seed=0)
+    enc = pc.PseudoEncoder(vd, local).to(dev)
+    dec = pc.PseudoDecoder(vd, local).to(dev)
+    pc.load_models(enc, p_enc, p_ent, "cuda:%d" % local)
+    pc.load_models(dec, p_dec, p_ent, "cuda:%d" % local)
+    out = {"config": "configs[0]: model-idx 3 --ssim (4_56), synthetic 512x1024 ERP, random-init weights, per GPU"}
+    for nimg in (1, 8):
+        g = torch.Generator(device=dev)
+        g.manual_seed(99 + rank)
+        low = torch.rand((nimg, 3, Hc // 32, Wc // 32), generator=g, device=dev)
+        x = (0.8 * torch.nn.functional.interpolate(low, size=(Hc, Wc), mode="bilinear", align_corners=False) +
+             0.2 * torch.rand((nimg, 3, Hc, Wc), generator=g, device=dev)).contiguous()
+        names = [os.path.join(d, "i%d.bin" % i) for i in range(nimg)]
+        res = {}
+        for tag, fn in (("encode", lambda: enc.encode_batch(x, names)), ("decode", lambda: dec.decode_batch(names, Hc, Wc))):
+            fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t0)
+            ts.sort()
+            v, _, sec = sharding.job_throughput(nimg * Hc * Wc / 1e6, ts[1], dev)
+            res[tag + "_MP/s"] = v
+            res[tag + "_ms"] = sec * 1e3
+        res["bpp"] = sum(os.path.getsize(n) for n in names) * 8.0 / (nimg * Hc * Wc)
+        out["batch%d" % nimg] = res
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_gpu(args):
     import torch
@@ -320,6 +360,16 @@ def run_gpu(args):
         e2e = {"value": mp_step / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 4 * CI * H * W * nimg,
                "d2h_bytes_per_step": 4 * CO * H * W * nimg, "ms_per_step": e_ms, "steps": e_steps, "checksum": checksum}
 
+    # ---- codec stages (BASELINE configs[0], model-idx 3 --ssim = prefix 4_56): full encode / decode of synthetic 512x1024 ERP
+    # images through PseudoEncoder / PseudoDecoder (transforms + context model + host range coder), one image and a batch of 8
+    # per GPU.  Informational: the headline `value` stays the configs[1] tile pipeline.
+    codec = None
+    if not args.no_codec:
+        try:
+            codec = time_codec(dev, local, rank, sharding)
+        except Exception as e:          # never lose the headline line to the extra measurement
+            codec = {"error": repr(e)[:200]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, sec, threads = time_cpu_port(5, 1)
@@ -332,7 +382,7 @@ def run_gpu(args):
                 "data": "synthetic", "config": {"workload": WORKLOAD, "images_per_gpu": nimg, "l2": "inputs (25.8 GB/GPU) exceed L2, no flush",
                                                 "parallelism": "image-sharded x%d, no collective" % world},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_hbm": roofline_hbm,
-                "cpu_baseline": cpu}
+                "cpu_baseline": cpu, "codec": codec}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -347,6 +397,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU per step (default: the config's 16)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-codec", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

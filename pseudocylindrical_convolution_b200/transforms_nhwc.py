@@ -86,9 +86,14 @@ class Runner:
         for v in views:
             self._live = [b for b in self._live if b is not v.buf]
 
-    def reset(self, device):
+    def reset(self, device, problem=None):
+        """problem = (batch, height, width) of the pass that starts; a different problem drops the pooled buffers of the
+        previous one (the pool is keyed by exact shape and would otherwise grow with every new image size)."""
         self.device = device
         self._live = []
+        if problem is not None and problem != getattr(self, "_problem", None):
+            self._pool.clear()
+            self._problem = problem
 
     # ------------------------------------------------------------------------------------------ parameters
     def packed(self, weight, ci_pad=None):
@@ -270,7 +275,7 @@ def _run_blocks(R, blocks, X, first_ci_pad=None):
 def encoder_forward(enc, erp, slice_op):
     """EncoderV2 (model_zoo_v2.py:129-151) on an ERP batch (N, 3, H, W) -> code (N*npart, code_channels, H/16/npart, W/16), NCHW."""
     R = enc._runner()
-    R.reset(erp.device)
+    R.reset(erp.device, tuple(erp.shape))
     npart = enc.npart
     N, Cin, H, W = erp.shape
     h = H // npart
@@ -293,7 +298,7 @@ def encoder_forward(enc, erp, slice_op):
 def decoder_forward(dec, code, uslice_op):
     """DecoderV2 (model_zoo_v2.py:189-211) + SphereUslice: code (N*npart, C, h, w) NCHW -> ERP (N, 3, 16 h npart, 16 w)."""
     R = dec._runner()
-    R.reset(code.device)
+    R.reset(code.device, tuple(code.shape))
     npart = dec.npart
     planes, Cc, h, W = code.shape
     x = R.plain(planes, h, W, Cc)

@@ -77,11 +77,11 @@ def main():
         del x
     H, W = 512, 1024
 
-    for N in (4, 8):
+    for N, H, W in ((4, 512, 1024), (8, 512, 1024), (16, 512, 1024), (2, 2048, 4096)):
         xs = torch.from_numpy(smooth_images(N, 3, H, W, seed=5)).to(dev)
         names = [os.path.join(d, "b%d.bin" % i) for i in range(N)]
-        for name, fn in (("batched encode %d x 512x1024" % N, lambda: enc.encode_batch(xs, names)),
-                         ("batched decode %d x 512x1024" % N, lambda: dec.decode_batch(names, H, W))):
+        for name, fn in (("batched encode %d x %dx%d" % (N, H, W), lambda: enc.encode_batch(xs, names)),
+                         ("batched decode %d x %dx%d" % (N, H, W), lambda: dec.decode_batch(names, H, W))):
             fn()
             torch.cuda.synchronize()
             ts = []
@@ -91,7 +91,9 @@ def main():
                 torch.cuda.synchronize()
                 ts.append(time.perf_counter() - t0)
             ts.sort()
-            print(json.dumps({"stage": name, "p50_ms": ts[1] * 1e3, "MP/s": N * H * W / 1e6 / ts[1]}))
+            print(json.dumps({"stage": name, "p50_ms": ts[1] * 1e3, "MP/s": N * H * W / 1e6 / ts[1]}), flush=True)
+        del xs
+        torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":
