@@ -163,7 +163,13 @@ __global__ void __launch_bounds__(256) ctx_conv_kernel(const float *__restrict__
 // only a handful of partial sums are live.  Chain lengths depend on (tc, kh, kw) only: no divergence inside a block.  Each
 // input value is loaded once (coalesced across the warp) for three FMAs; the weights of the block's (net, tc) sit in shared
 // memory as one float4 per (channel, tap) and are read as warp-uniform 128-bit broadcasts.
-constexpr int CT_CPT = 4;          // cells per thread
+#ifndef PCX_CT_CPT
+#define PCX_CT_CPT 4
+#endif
+#ifndef PCX_CT_MINB
+#define PCX_CT_MINB 4
+#endif
+constexpr int CT_CPT = PCX_CT_CPT;  // cells per thread
 constexpr int CT_WARPS = 4;        // warps (= row tiles of 32*CPT columns) per block
 
 struct CtAcc { float v[CT_CPT][3]; };
@@ -242,7 +248,7 @@ struct CtTree<GI, T, 32> {
 };
 
 template <int GI>
-__global__ void __launch_bounds__(32 * CT_WARPS) ctx_conv_tiled_kernel(const float *__restrict__ in, const float *__restrict__ weight,
+__global__ void __launch_bounds__(32 * CT_WARPS, PCX_CT_MINB) ctx_conv_tiled_kernel(const float *__restrict__ in, const float *__restrict__ weight,
                                                                        const float *__restrict__ bias, const float *__restrict__ act,
                                                                        const float *__restrict__ addsrc, float *__restrict__ out,
                                                                        int nimg, int npart, int G, int h, int W, int pad_in,
@@ -265,7 +271,9 @@ __global__ void __launch_bounds__(32 * CT_WARPS) ctx_conv_tiled_kernel(const flo
     const int rt = blockIdx.x * CT_WARPS + warp;
     const int Hf = h * npart;
     if (rt >= Hf * ntile) return;
-    const int hp = rt / ntile, x0 = (rt % ntile) * 32 * CT_CPT;
+    // consecutive warps (and blocks) take consecutive ROWS of one column tile: their 5-row windows overlap, so the block's
+    // working set stays L1-resident
+    const int hp = rt % Hf, x0 = (rt / Hf) * 32 * CT_CPT;
     const int g = hp / h, th = hp % h, wl = bands.wl[g];
     if (x0 >= wl) return;
     const i64 ih = h + 2 * pad_in, iw = W + 2 * pad_in;
