@@ -692,21 +692,43 @@ __device__ __forceinline__ void reg_fence7(float (&a)[7])
 {
     asm volatile("" : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]));
 }
-// 128-bit load, program-ordered among its kind; with on == 0 nothing is loaded and the result is +0.  L1-cached (.ca) on
-// purpose: inside one launch every scratch buffer is written in exactly one phase and read only in later ones, behind a grid
-// barrier with acquire semantics, and L1 starts clean at every launch - a cached line can never be stale, and the 5x5 windows
-// of neighbouring cells (handled by warps of the same block) overlap by two thirds.
-__device__ __forceinline__ float4 ld_cg_v4_ordered(const float *p, int on)
+// NQ consecutive 128-bit loads from one base address in ONE asm statement (one predicate, immediate offsets, issued back to
+// back; volatile keeps them ahead of the arithmetic that follows).  With on == 0 nothing is loaded and v is left untouched -
+// the caller never consumes it.  L1-cached (.ca) on purpose: inside one launch every scratch buffer is written in exactly one
+// phase and read only in later ones, behind a grid barrier with acquire semantics, and L1 starts clean at every launch - a
+// cached line can never be stale, and the 5x5 windows of neighbouring cells (warps of the same block) overlap by two thirds.
+__device__ __forceinline__ void ld_ca_v4x2(float4 (&v)[2], const float *p, int on)
 {
-    float4 v;
     asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.s32 p, %5, 0;\nmov.f32 %0, 0f00000000;\nmov.f32 %1, 0f00000000;\nmov.f32 %2, 0f00000000;\n"
-        "mov.f32 %3, 0f00000000;\n@p ld.global.ca.v4.f32 {%0, %1, %2, %3}, [%4];\n}"
-        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+        "{\n.reg .pred p;\nsetp.ne.s32 p, %9, 0;\n"
+        "@p ld.global.ca.v4.f32 {%0, %1, %2, %3}, [%8];\n"
+        "@p ld.global.ca.v4.f32 {%4, %5, %6, %7}, [%8+16];\n}"
+        : "+f"(v[0].x), "+f"(v[0].y), "+f"(v[0].z), "+f"(v[0].w), "+f"(v[1].x), "+f"(v[1].y), "+f"(v[1].z), "+f"(v[1].w)
         : "l"(p), "r"(on)
         : "memory");
-    return v;
 }
+__device__ __forceinline__ void ld_ca_v4x6(float4 (&v)[6], const float *p, int on)
+{
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.s32 p, %25, 0;\n"
+        "@p ld.global.ca.v4.f32 {%0, %1, %2, %3}, [%24];\n"
+        "@p ld.global.ca.v4.f32 {%4, %5, %6, %7}, [%24+16];\n"
+        "@p ld.global.ca.v4.f32 {%8, %9, %10, %11}, [%24+32];\n"
+        "@p ld.global.ca.v4.f32 {%12, %13, %14, %15}, [%24+48];\n"
+        "@p ld.global.ca.v4.f32 {%16, %17, %18, %19}, [%24+64];\n"
+        "@p ld.global.ca.v4.f32 {%20, %21, %22, %23}, [%24+80];\n}"
+        : "+f"(v[0].x), "+f"(v[0].y), "+f"(v[0].z), "+f"(v[0].w), "+f"(v[1].x), "+f"(v[1].y), "+f"(v[1].z), "+f"(v[1].w),
+          "+f"(v[2].x), "+f"(v[2].y), "+f"(v[2].z), "+f"(v[2].w), "+f"(v[3].x), "+f"(v[3].y), "+f"(v[3].z), "+f"(v[3].w),
+          "+f"(v[4].x), "+f"(v[4].y), "+f"(v[4].z), "+f"(v[4].w), "+f"(v[5].x), "+f"(v[5].y), "+f"(v[5].z), "+f"(v[5].w)
+        : "l"(p), "r"(on)
+        : "memory");
+}
+template <int NQ>
+__device__ __forceinline__ void ld_ca_batch(float4 (&v)[NQ], const float *p, int on);
+template <>
+__device__ __forceinline__ void ld_ca_batch<2>(float4 (&v)[2], const float *p, int on) { ld_ca_v4x2(v, p, on); }
+template <>
+__device__ __forceinline__ void ld_ca_batch<6>(float4 (&v)[6], const float *p, int on) { ld_ca_v4x6(v, p, on); }
 __device__ __forceinline__ void reg_fence_v4(float4 &a, float4 &b)
 {
     asm volatile("" : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w), "+f"(b.x), "+f"(b.y), "+f"(b.z), "+f"(b.w));
@@ -787,15 +809,10 @@ __device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLaye
             const int on = nk > c0;
             float4 xa[NQ], xb[NQ];
 #pragma unroll
-            for (int q = 0; q < NQ; q++) xa[q] = ld_cg_v4_ordered(tp.pa + c0 * GI + 4 * q, on && tp.mode != 2);
-#pragma unroll
-            for (int q = 0; q < NQ; q++) xb[q] = ld_cg_v4_ordered(tp.pb + c0 * GI + 4 * q, on && tp.mode != 0);
-            // every activation load of the batch is in flight before the first FFMA can wait on one
-#pragma unroll
-            for (int q = 0; q < NQ; q += 2) {
-                reg_fence_v4(xa[q], xa[q + 1]);
-                reg_fence_v4(xb[q], xb[q + 1]);
-            }
+            for (int q = 0; q < NQ; q++) xa[q] = xb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            // both batches of 128-bit loads are in flight before the first FFMA can wait on one
+            ld_ca_batch<NQ>(xa, tp.pa + c0 * GI, on && tp.mode != 2);
+            ld_ca_batch<NQ>(xb, tp.pb + c0 * GI, on && tp.mode != 0);
             float va[8 * GI];
 #pragma unroll
             for (int q = 0; q < NQ; q++) { va[4 * q] = xa[q].x; va[4 * q + 1] = xa[q].y; va[4 * q + 2] = xa[q].z; va[4 * q + 3] = xa[q].w; }
@@ -1383,6 +1400,10 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
             const int ntile = n.W / (32 * CT_CPT);
             dim3 grid((unsigned)ceil_div((i64)Hf * ntile, CT_WARPS), (unsigned)n.G, (unsigned)nrep);
             const size_t smem = (size_t)Ci * 25 * sizeof(float4);
+            if (smem > 48 * 1024) {                       // 48 channel groups (valid_dim 192): 57.6 KB of weight rows
+                PCX_CUDA(cudaFuncSetAttribute(ctx_conv_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                PCX_CUDA(cudaFuncSetAttribute(ctx_conv_tiled_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            }
             if (l.gi == 1)
                 ctx_conv_tiled_kernel<1><<<grid, 32 * CT_WARPS, smem, s>>>(l.in, l.weight, l.bias, l.act, l.add, l.out, n.nimg, n.npart, n.G,
                                                                           n.h, n.W, n.pad, l.pad_out, l.constrain, bands);

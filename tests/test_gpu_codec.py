@@ -286,3 +286,46 @@ def test_fused_step_decoder_equals_operator_sequence(codec, tmp_path):
                 assert launches <= 204 + 8, launches          # one launch per step (+ the final DInput2 / fill)
     finally:
         lib.pcx_wave_set_fused(1)
+
+
+@pytest.mark.parametrize("vd,prex,Hs,Ws", [(112, "5_112", 512, 1024), (192, "8_192", 256, 512)])
+def test_other_model_sizes_round_trip(cuda, tmp_path, vd, prex, Hs, Ws):
+    """model-idx 4..8 use 112 / 192 code channels (28 / 48 channel groups in the context model): every engine must handle them
+    (larger weight rows in shared memory, longer chains) - symbols decode losslessly in all decoder modes and the one-shot
+    and stepwise encoders agree."""
+    import torch
+    from pseudocylindrical_convolution_b200 import _lib, config, pseudo_codec as pc
+    from pseudocylindrical_convolution_b200.random_init import synthesize_checkpoints
+    d = str(tmp_path)
+    p_enc, p_dec, p_ent = synthesize_checkpoints(d, prex, vd, 0, seed=3)
+    enc = pc.PseudoEncoder(vd, 0).to(cuda)
+    dec = pc.PseudoDecoder(vd, 0).to(cuda)
+    pc.load_models(enc, p_enc, p_ent, "cuda:0")
+    pc.load_models(dec, p_dec, p_ent, "cuda:0")
+    x = torch.from_numpy(smooth_images(2, 3, Hs, Ws, seed=21)).to(cuda)
+    sym = enc.symbols(x)
+    assert tuple(sym.shape) == (32, vd // 4, Hs // 128, Ws // 8)
+    streams = {}
+    try:
+        for full in (1, 0):
+            config.WAVE_ENCODE_FULL = full
+            names = [str(tmp_path / ("m%d_%d.bin" % (full, i))) for i in range(2)]
+            enc.ent.encode_batch(sym.clone(), names)
+            streams[full] = [open(n, "rb").read() for n in names]
+    finally:
+        config.WAVE_ENCODE_FULL = 1
+    assert streams[0] == streams[1] and len(streams[0][0]) > 100
+    # What the coder sees is the PseudoFill'ed tensor (pseudo_codec.py:99).  For widths that are not a multiple of 1024 the band
+    # widths at the code scale do not double exactly into those of the context scale (SURVEY.md A.1: 2*round(7.5) != 15), so
+    # a column the quantiser filled can lie outside the context geometry - the reference drops it the same way.
+    want = enc.ent.fill(sym.clone())
+    lib = _lib.load()
+    try:
+        for fused in (1, 0):
+            lib.pcx_wave_set_fused(fused)
+            got = dec.ent.decode_batch(Hs // 128, Ws // 8, names)
+            assert torch.equal(got, want), "vd %d fused %d" % (vd, fused)
+    finally:
+        lib.pcx_wave_set_fused(1)
+    rec = dec.decode_batch(names, Hs, Ws)
+    assert tuple(rec.shape) == (2, 3, Hs, Ws) and torch.isfinite(rec).all()
