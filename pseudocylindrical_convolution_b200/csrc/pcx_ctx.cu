@@ -12,6 +12,7 @@
 #include <thread>
 #include <chrono>
 #include <string.h>
+#include <math.h>
 #include <vector>
 
 namespace {
@@ -605,6 +606,8 @@ struct StepNet {
     Bands bands;
     const int *hband, *hrow, *hcol, *order;
     const float *htw;
+    const int4 *cell;           // per entry of `order`: (col, global row, band, row in band) - no integer division on the hot path
+    float halo_one;             // smallest float f with (double)f >= 1 - 1e-6: the "no causal source" test of pcx_ctx_pad_items
     float *sym_nchw;            // layers[0].in of the caller (NCHW, padded): receives symbol + input_bias for the Python side
     const float *prev;          // symbols decoded at the previous step, (image, cell of the window) - mapped host memory
     int *cdf;                   // CDF rows of this step, (image, cell of the window) x (nstep+1) - mapped host memory
@@ -612,6 +615,14 @@ struct StepNet {
     unsigned long long *dbg;    // optional: globaltimer of block 0 at kernel entry, after every barrier and at exit (PCX_WAVE_TRACE)
     StepLayer L[PCX_WAVE_MAX_LAYERS];
 };
+
+__global__ void step_cellinfo_kernel(const int *__restrict__ order, int4 *__restrict__ cell, int n, int h, int W)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int hw = order[i], tw = hw % W, hp = hw / W;
+    cell[i] = make_int4(tw, hp, hp / h, hp % h);
+}
 
 __device__ __forceinline__ void step_stamp(const StepNet &d, int step, int slot)
 {
@@ -622,6 +633,9 @@ __device__ __forceinline__ void step_stamp(const StepNet &d, int step, int slot)
     }
 }
 
+// Arrive with a release reduction, poll with RELAXED loads and fence once after the exit: an acquire load in the spin loop
+// makes every poll invalidate the SM's L1 (CCTL.IVALL, 1.5 M per launch in the first profile) under the other resident block
+// that is still computing on L1-cached activations.
 __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned target)
 {
     __syncthreads();
@@ -629,8 +643,9 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned target)
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         unsigned v;
         do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
         } while ((int)(v - target) < 0);
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
     __syncthreads();
 }
@@ -670,7 +685,7 @@ __device__ __forceinline__ StepTap step_resolve(const StepNet &d, const float *i
     const i64 e = (i64)hr * W + xi;
     const int q = d.hcol[e];
     const float t = d.htw[e];
-    if (q < 0 && (double)t >= 1 - 1e-6) return r;                // no causal source: the cell stays 0
+    if (q < 0 && t >= d.halo_one) return r;                      // no causal source: the cell stays 0
     const float *srow = in + (((pn * d.npart + pg) * ih + d.hrow[hr] + pad) * iw + pad) * cp;
     const int q1 = (q + 1 == d.bands.wl[pg]) ? 0 : q + 1;
     r.pa = srow + (i64)(q < 0 ? 0 : q) * cp;
@@ -737,9 +752,11 @@ __device__ __forceinline__ void reg_fence_v4(float4 &a, float4 &b)
 // The block's share of a step: one (net image pn, plane) pair and a run of that plane's cells.  All cells of a plane carry
 // the same channel group tc = step - plane, so the three output rows of (net, tc) are the only weights the block needs:
 // they are staged in shared memory with cp.async one layer AHEAD (weights do not depend on the grid barrier).
-struct StepChunk { int net, plane, cell0, ncell; };   // cells cell0 .. cell0+ncell of the plane's (image, cell) list
+struct StepChunk { int net, plane, cell0, ncell, img0, rem0; };   // cells cell0 .. cell0+ncell of the plane's (image, cell) list;
+                                                                  // cell0 = img0 * cells_of_plane + rem0
 
 constexpr int STEP_THREADS = 256;
+constexpr int STEP_MAX_RUNS = 32;  // runs of a block whose descriptors are cached in shared memory
 
 __device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc)
 {
@@ -788,10 +805,11 @@ __device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLaye
     gmax = gmax > G ? G : gmax;
     const float4 *wl_ = reinterpret_cast<const float4 *>(ws) + kh * 5 + kw;
     for (int k = warp; k < ch.ncell; k += nwarp) {
-        const int e = ch.cell0 + k, img = e / pcells;
+        int img = ch.img0, ce = ch.rem0 + k;                     // (image, cell of the plane) of entry cell0 + k
+        while (ce >= pcells) { ce -= pcells; img++; }
         const int pn = ch.net * d.nimg + img;
-        const int hw = d.order[first + e - img * pcells];
-        const int tw = hw % W, hp = hw / W, g = hp / h, th = hp % h;
+        const int4 ci = d.cell[first + ce];
+        const int tw = ci.x, g = ci.z, th = ci.w;
         StepTap tp;
         tp.pa = tp.pb = l.in;
         tp.t = 0.f;
@@ -881,14 +899,17 @@ __device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLaye
 // list of nimg * cells entries, cut into runs of at most S
 __device__ __forceinline__ StepChunk step_chunk_of(const int *__restrict__ start, int id, int p0, int np, int S, int nb, int nimg)
 {
-    StepChunk c = {0, p0, 0, 0};
+    StepChunk c = {0, p0, 0, 0, 0, 0};
     for (int q = p0; q < p0 + np; q++) {
-        const int cells = (start[q + 1] - start[q]) * nimg;
+        const int pc = start[q + 1] - start[q];
+        const int cells = pc * nimg;
         const int nrun = (cells + S - 1) / S;
         if (id < nrun * nb) {
             const int run = id % nrun;
             c.net = id / nrun; c.plane = q; c.cell0 = run * S;
             c.ncell = cells - run * S < S ? cells - run * S : S;
+            c.img0 = c.cell0 / pc;
+            c.rem0 = c.cell0 - c.img0 * pc;
             return c;
         }
         id -= nrun * nb;
@@ -912,8 +933,14 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_step_kernel(const __grid_co
     const int first = start[p0], count = start[p0 + np] - start[p0];
     const int nmy = blockIdx.x < nchunk ? (nchunk - 1 - blockIdx.x) / gridDim.x + 1 : 0;      // my runs per layer
     const int nitems = nmy * d.nlayers;
+    // the block's runs are the same for every layer: decode them ONCE (the walk over the planes costs three integer
+    // divisions per plane - done per item by every thread it was half of the kernel's instructions)
+    __shared__ StepChunk s_chunk[STEP_MAX_RUNS];
+    if (threadIdx.x < nmy && threadIdx.x < STEP_MAX_RUNS)
+        s_chunk[threadIdx.x] = step_chunk_of(start, blockIdx.x + threadIdx.x * gridDim.x, p0, np, S, d.nb, d.nimg);
+    __syncthreads();
     if (nitems > 0) {
-        const StepChunk c0 = step_chunk_of(start, blockIdx.x, p0, np, S, d.nb, d.nimg);
+        const StepChunk c0 = s_chunk[0];
         step_stage_weights(d, d.L[0], c0.net, step - c0.plane, step_ws, wstride);
     }
     cp_async_commit();
@@ -925,8 +952,8 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_step_kernel(const __grid_co
         float *out = const_cast<float *>(d.L[0].in);
         for (int t = gtid; t < pcount * d.nimg; t += nthr) {
             const int k = t % pcount, n = t / pcount;
-            const int hw = d.order[pfirst + k];
-            const int tw = hw % W, hp = hw / W, g = hp / h, th = hp % h;
+            const int4 ci = d.cell[pfirst + k];
+            const int tw = ci.x, hp = ci.y, g = ci.z, th = ci.w;
             const int tc = step - 1 - tw - hp;
             const float v = __fadd_rn(d.prev[t], d.input_bias);
             const i64 i = ((((i64)n * d.npart + g) * ih + th + pad) * iw + tw + pad) * cp0 + tc;
@@ -941,11 +968,11 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_step_kernel(const __grid_co
     int it = 0;
     for (int L = 0; L < d.nlayers; L++) {
         for (int ci = 0; ci < nmy; ci++, it++) {
-            const StepChunk ch = step_chunk_of(start, blockIdx.x + ci * gridDim.x, p0, np, S, d.nb, d.nimg);
+            const StepChunk ch = ci < STEP_MAX_RUNS ? s_chunk[ci] : step_chunk_of(start, blockIdx.x + ci * gridDim.x, p0, np, S, d.nb, d.nimg);
             if (ci > 0) __syncthreads();               // every warp is done with item it-1: its buffer may be refilled
             if (it + 1 < nitems) {
                 const int nci = ci + 1 < nmy ? ci + 1 : 0, nL = ci + 1 < nmy ? L : L + 1;
-                const StepChunk nc = step_chunk_of(start, blockIdx.x + nci * gridDim.x, p0, np, S, d.nb, d.nimg);
+                const StepChunk nc = nci < STEP_MAX_RUNS ? s_chunk[nci] : step_chunk_of(start, blockIdx.x + nci * gridDim.x, p0, np, S, d.nb, d.nimg);
                 step_stage_weights(d, d.L[nL], nc.net, step - nc.plane, step_ws + ((it + 1) & 1) * (4 * wstride + 8), wstride);
             }
             cp_async_commit();
@@ -964,8 +991,8 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_step_kernel(const __grid_co
     const StepLayer &last = d.L[d.nlayers - 1];
     for (int t = gtid; t < count * d.nimg; t += nthr) {
         const int k = t % count, img = t / count;
-        const int hw = d.order[first + k];
-        const int tw = hw % W, hp = hw / W, g = hp / h, th = hp % h;
+        const int4 ci = d.cell[first + k];
+        const int tw = ci.x, hp = ci.y, g = ci.z, th = ci.w;
         const int tc = step - tw - hp;
         float w[3], dl[3], mu[3];                          // ng == 3, nstep == 8 (checked by the launcher)
 #pragma unroll
@@ -1523,7 +1550,9 @@ static int wave_decode_fused(const pcx_wave_net &n, pcx_coder *const *coders, lo
     off[1] = in_elems * G8 * n.layers[0].gi;
     for (int L = 0; L < n.nlayers; L++)
         off[L + 2] = off[L + 1] + planes * (n.h + 2 * n.layers[L].pad_out) * (n.W + 2 * n.layers[L].pad_out) * G8 * 3;
-    const size_t need_bytes = sizeof(float) * (size_t)off[n.nlayers + 1] + 256;
+    const int ncell_total = n.h_start[Hf + n.W - 1];                              // valid cells of one image
+    const size_t cell_off = (sizeof(float) * (size_t)off[n.nlayers + 1] + 255) / 256 * 256;
+    const size_t need_bytes = cell_off + sizeof(int4) * (size_t)ncell_total + 256;
     if (need_bytes > g_step_scratch_bytes) {
         if (g_step_scratch) cudaFree(g_step_scratch);
         g_step_scratch = nullptr;
@@ -1551,6 +1580,15 @@ static int wave_decode_fused(const pcx_wave_net &n, pcx_coder *const *coders, lo
                     "layer %d must read the padded output of layer %d", L, L - 1);
     }
     d.sym_nchw = n.layers[0].in;
+    int4 *d_cell = reinterpret_cast<int4 *>(reinterpret_cast<char *>(g_step_scratch) + cell_off);
+    step_cellinfo_kernel<<<ceil_div(ncell_total, 256), 256, 0, s>>>(n.d_order, d_cell, ncell_total, n.h, n.W);
+    PCX_LAUNCHED();
+    d.cell = d_cell;
+    {
+        float f = (float)(1 - 1e-6);
+        if ((double)f < 1 - 1e-6) f = nextafterf(f, 2.0f);
+        d.halo_one = f;
+    }
     PCX_CUDA(cudaMemsetAsync(n.layers[0].in, 0, sizeof(float) * (size_t)nrep * n.npart * n.G * (n.h + 2 * n.pad) * (n.W + 2 * n.pad), s));
 
     const int threads = STEP_THREADS;
