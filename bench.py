@@ -321,7 +321,9 @@ def run_gpu(args):
             traffic = json.load(f).get("conv_dram_bytes_per_launch")
     roofline = {"kernel": "conv_pair_kernel<192> (tcgen05 cta_group::2 kind::tf32, 256x192 tiles per CTA pair, halo-tile taps)", "bound": "tensor", "achieved": conv_tflops,
                 "peak": tf32_peak, "unit": "TFLOP/s", "frac": conv_tflops / tf32_peak, "traffic": traffic,
-                "peak_source": "%s bf16_tflops_sustained / 2 (tf32 issues at half the f16 rate)" % peaks["source"],
+                "peak_source": "%s bf16_tflops_sustained / 2 (tf32 issues at half the f16 rate; the kernel is timed inside a long step). "
+                               "frac > 1 = faster than half of cuBLAS's sustained bf16 rate" % peaks["source"],
+                "peak_burst": peaks["bf16"] / 2.0, "frac_of_burst": conv_tflops / (peaks["bf16"] / 2.0),
                 "flops_per_launch": flops_conv, "avg_launch_ms": k_ms["conv"], "share_of_step": k_ms["conv"] * nimg / ms}
     bytes_sp = 4.0 * (CI * H * W + CI * sum((h + 2) * (w + 2) for w in wl))          # read ERP + write valid padded tiles
     bytes_us = 4.0 * (CO * valid + CO * H * W)                                          # read valid tiles + write ERP
