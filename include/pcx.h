@@ -277,6 +277,22 @@ int pcx_gmm_table(float *d_logit, float *d_delta, const float *d_mean, int n, in
 int pcx_gmm_nll(const float *d_w, const float *d_delta, const float *d_mean, const float *d_label,
                 float *d_loss, int n, int ng, void *stream);
 
+/* ---- evaluation metrics of `pseudo_codec.py --test` --------------------------------
+ * ProjectsOp (main.cpp:30-35 -> extension/projects_cuda.cu): 14 rectilinear viewports of an ERP image.
+ * pcx_project_table: projects_opt::init + update (:96-152) - theta / phi / fov in units of pi (projects.hpp:8-19);
+ * d_tf (14, h_out*w_out, 2) ERP pixel coordinates.  pcx_project_fwd: forward_cuda (:215-246), bilinear (wrap in longitude,
+ * clamp in latitude) or nearest; d_out is (14, N*C, h_out, w_out) exactly as the reference kernel writes it. */
+int pcx_project_table(const float *theta, const float *phi, float fov, int h_out, int w_out, int H, int W, float *d_tf, void *stream);
+int pcx_project_fwd(const float *d_in, const float *d_tf, float *d_out, int N, int C, int H, int W, int h_out, int w_out, int nearest,
+                    void *stream);
+/* Gaussian-window SSIM (PCONV_operator/pytorch_ssim.py:17-37: window 11, sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2):
+ * *d_mean = mean of the SSIM map over planes*h*w; d_map (optional) receives the map; d_scratch: >= ceil(planes*h*w/256)
+ * doubles.  pcx_mean_sqdiff: mean((a-b)^2) (d_b != NULL, the viewport MSE of pseudo_codec.py:276) or mean(a). */
+int pcx_ssim(const float *d_a, const float *d_b, long long planes, int h, int w, int window, float sigma, float *d_map,
+             double *d_scratch, long long scratch_len, double *d_mean, void *stream);
+int pcx_mean_sqdiff(const float *d_a, const float *d_b, long long total, double *d_scratch, long long scratch_len, double *d_mean,
+                    void *stream);
+
 /* ---- host arithmetic coder (coder/python.cpp:63-72 `coder.coder`) --------------------------------------
  * 32-bit-state range coder, MSB-first bit stream, no header, one terminating 1 bit then zero padding
  * (coder/ArithmeticCoder.cpp:34-69, :82-116, :152-154; coder/BitIoStream.cpp:52-72). */

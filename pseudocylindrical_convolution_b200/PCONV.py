@@ -654,8 +654,38 @@ class _OutOfScope:
         raise NotImplementedError("%s is outside the codec hot path (%s); see DESIGN.md 'Out of scope'" % (type(self).__name__, self.what))
 
 
-class ProjectsOp(_OutOfScope):
-    what = "viewport metric, extension/projects_cuda.cu"
+class ProjectsOp(_Op):
+    """projects_opt (extension/projects.hpp): ProjectsOp(h_out, w_out, theta[14], phi[14], fov, near, device, timeit) - the 14
+    rectilinear viewports on which `pseudo_codec.py --test` measures PSNR / SSIM.  forward only (metric)."""
+
+    def __init__(self, h_out, w_out, theta, phi, fov=0.33333, near=False, device=0, timeit=False):
+        super().__init__(device, timeit)
+        self.h_out_, self.w_out_, self.fov_, self.near_ = int(h_out), int(w_out), float(fov), bool(near)
+        if len(theta) < 14 or len(phi) < 14:
+            raise PcxError("ProjectsOp needs 14 viewport angles (extension/projects.hpp:10-13)")
+        self.theta_, self.phi_ = [float(v) for v in theta[:14]], [float(v) for v in phi[:14]]
+        self._tf = {}
+
+    def _on_device_change(self):
+        self._tf.clear()
+
+    def forward(self, x):
+        _check_tensor(x)
+        N, Cc, H, W = x.shape
+        with torch.cuda.device(x.device):
+            key = (H, W)
+            if key not in self._tf:          # projects_opt::reshape -> update (projects_cuda.cu:153-161)
+                tf = torch.zeros((14, self.h_out_ * self.w_out_, 2), dtype=torch.float32, device=x.device)
+                call("pcx_project_table", (C.c_float * 14)(*self.theta_), (C.c_float * 14)(*self.phi_), C.c_float(self.fov_),
+                     self.h_out_, self.w_out_, H, W, _p(tf), _stream())
+                self._tf[key] = tf
+            out = self._out("top", (N * 14, Cc, self.h_out_, self.w_out_), x)
+            call("pcx_project_fwd", _p(x), _p(self._tf[key]), _p(out), N, Cc, H, W, self.h_out_, self.w_out_, 1 if self.near_ else 0,
+                 _stream())
+        return [out]
+
+    def backward(self, g):
+        raise PcxError("ProjectsOp.backward is training-only and not built (extension/projects_cuda.cu:247-329)")
 
 
 class ContextReshapeOp(_OutOfScope):

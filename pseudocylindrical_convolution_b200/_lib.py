@@ -87,6 +87,10 @@ PROTOTYPES = {
     "pcx_wave_decode": (_I, [C.POINTER(WaveNet), C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), _P]),
     "pcx_gmm_table": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _I, _P, _P, _P]),
     "pcx_gmm_nll": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
+    "pcx_project_table": (_I, [_FP, _FP, _F, _I, _I, _I, _I, _P, _P]),
+    "pcx_project_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "pcx_ssim": (_I, [_P, _P, C.c_longlong, _I, _I, _I, _F, _P, _P, C.c_longlong, _P, _P]),
+    "pcx_mean_sqdiff": (_I, [_P, _P, C.c_longlong, _P, C.c_longlong, _P, _P]),
     "pcx_coder_open": (_P, [C.c_char_p]),
     "pcx_coder_close": (None, [_P]),
     "pcx_coder_start_encoder": (_I, [_P]),

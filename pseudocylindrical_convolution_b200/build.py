@@ -13,7 +13,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(PKG, "libpcx.so")
 
-SOURCES = ["pcx_geometry.cu", "pcx_tile.cu", "pcx_tile_nhwc.cu", "pcx_quant.cu", "pcx_dense.cu", "pcx_conv_tc.cu", "pcx_nhwc_ops.cu", "pcx_ctx.cu",
+SOURCES = ["pcx_geometry.cu", "pcx_tile.cu", "pcx_tile_nhwc.cu", "pcx_quant.cu", "pcx_dense.cu", "pcx_conv_tc.cu", "pcx_nhwc_ops.cu", "pcx_ctx.cu", "pcx_metrics.cu",
            "pcx_coder.cpp"]
 HEADERS = [os.path.join(CSRC, "pcx_common.cuh"), os.path.join(PKG, "..", "include", "pcx.h")]
 

@@ -4,7 +4,7 @@
 EntropyConvDBT, EntropyResidualBlockDBT, EntEncoder, EntDecoder, PseudoEncoder, PseudoDecoder keep their names,
 constructor arguments and state_dict keys.  Differences: sizes are not hard-wired to 512x1024 (the code size is
 derived from the input / passed to the decoder), only the rows the coder needs cross PCIe each wavefront step,
-and the metrics of --test are computed on the ERP image (the viewport projector is out of scope).
+and --test evaluates PSNR / SSIM on the reference's 14 viewports with this package's own projector and SSIM kernels.
 """
 import argparse
 import math
@@ -339,24 +339,36 @@ def decoding(code_list, decoded_img_list, model_idx=0, mse=True, device_id=0):
 
 
 def decoding_and_test(code_list, img_list, model_idx=0, mse=True, device_id=0):
-    """Decode and report bitrate / PSNR on the ERP image.  The reference evaluates PSNR/SSIM on 14 rectilinear
-    viewports (MultiProject + SSIM, pseudo_codec.py:270-284); that projector is out of scope here."""
+    """Decode and report bitrate, viewport PSNR and viewport SSIM like the reference (pseudo_codec.py:262-290): source and
+    reconstruction are sampled on 14 rectilinear viewports of 171 x 256 pixels (MultiProject, fov 0.5 pi), PSNR from the
+    mean squared difference, SSIM with an 11-tap Gaussian window."""
     import cv2
+    from .PCONV_operator import MultiProject, SSIM
+    from .PCONV_operator.pytorch_ssim import mean_squared_difference
     prex, vd, model_dir = _select(model_idx, mse)
     cuda = 'cuda:{}'.format(device_id)
     t1 = PseudoDecoder(vd, device_id=device_id).to(cuda)
     load_models(t1, '{}/{}_decoder.pt'.format(model_dir, prex), '{}/{}_ent.pt'.format(model_dir, prex), cuda)
-    rt_list, pr_list = [], []
+    pr1 = MultiProject(171, int(171 * 1.5), 0.5, False, device_id).to(cuda)
+    pr2 = MultiProject(171, int(171 * 1.5), 0.5, False, device_id).to(cuda)
+    sim_func = SSIM(11, 3).to(cuda)
+    rt_list, pr_list, ssim_list = [], [], []
     for fc, fn in zip(code_list, img_list):
         rdata = t1(fc)
         data = img2tensor(check_img(cv2.imread(fn)), cuda)
-        pr = psnr_f(torch.mean((data - rdata) ** 2).item())
+        x = pr1(data)
+        y = pr2(rdata)
+        pr = psnr_f(mean_squared_difference(x, y).item())
+        vssim = sim_func(x, y).item()
         rt = os.path.getsize(fc) * 8 / 1024. / 512.
         rt_list.append(rt)
         pr_list.append(pr)
-        print('Decoding {}, compare it to {} \n Bitrate:{:.3f}bpp, ERP-PSNR:{:.2f}dB'.format(fc, fn, rt, pr))
+        ssim_list.append(vssim)
+        print('Decoding {}, compare it to {} \n Bitrate:{:.3f}bpp, PSNR:{:.2f}dB, SSIM:{:.4f}'.format(fc, fn, rt, pr, vssim))
     print('-' * 53 + '\nAverage Performance\n' + '-' * 53)
-    print('Bitrate:{:.3f}bpp, ERP-PSNR:{:.2f}dB'.format(float(np.mean(rt_list)), float(np.mean(pr_list))))
+    rt, pr, vssim = float(np.mean(rt_list)), float(np.mean(pr_list)), float(np.mean(ssim_list))
+    print('Bitrate:{:.3f}bpp, PSNR:{:.2f}dB, SSIM:{:.4f}'.format(rt, pr, vssim))
+    return rt, pr, vssim
 
 
 def read_list(fname):
