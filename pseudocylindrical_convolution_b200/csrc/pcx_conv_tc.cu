@@ -27,7 +27,8 @@ constexpr int BLOCK_M = 128;          // pixels per tile
 constexpr int BLOCK_K = 32;           // input channels per pipeline stage (= one 128-byte swizzled row)
 constexpr int UMMA_K = 8;             // tf32
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;     // 16 KB: 128 pixel rows x 128 B
-constexpr int NUM_THREADS = 192;      // 6 warps
+constexpr int NUM_THREADS = 192;      // 6 warps (CTA-pair kernel: 4 epilogue warps per CTA, 8 per pair)
+constexpr int TC_THREADS = 320;       // single-CTA kernel: producer, MMA issuer + EIGHT epilogue warps (two per TMEM lane quadrant)
 constexpr int MAX_CO_STAGED = 768;    // bias + PReLU slope vectors staged in shared memory (2 x 3 KB)
 constexpr int VEC_SMEM = 2 * MAX_CO_STAGED * 4 + 4 * 32 * 36 * 4;   // + the epilogue warps' transpose tiles
 
@@ -48,9 +49,9 @@ template <int NT>
 struct Cfg {
     static constexpr int B_STAGE_BYTES = NT * BLOCK_K * 4;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = (184 * 1024) / STAGE_BYTES > 8 ? 8 : (184 * 1024) / STAGE_BYTES;
     static constexpr int TMEM_COLS = NT * 2 <= 32 ? 32 : (NT * 2 <= 64 ? 64 : (NT * 2 <= 128 ? 128 : (NT * 2 <= 256 ? 256 : 512)));
-    static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ + VEC_SMEM;
+    static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ + VEC_SMEM + 4 * 32 * 36 * 4 /*8 epilogue warps*/;
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -186,6 +187,23 @@ __device__ __forceinline__ bool tile_live(const TcParams &p, const Tile &t)
 // store is four full 128-byte lines.  Math order per element is unchanged: +bias, act, *mul, +residual, fill.
 // `bias` / `slope` point to the per-channel vectors staged in SHARED memory (broadcast LDS; the global copies would be
 // re-fetched from L2 after every cluster-scope acquire, which invalidates L1).
+// Transcendental epilogues on the SFU (MUFU.RSQ / SQRT / EX2 / RCP, ~1e-7 relative error): the operands of these layers
+// went through TF32 tensor-core products (1e-3), and the IEEE-rounded 1/sqrtf / expf / division sequences (~43 instructions
+// per channel) made the GDN epilogue issue-bound - as expensive as the HBM traffic of the layer (SASS count, r1y).
+__device__ __forceinline__ float fast_rsqrt(float x)
+{
+    float r;
+    asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_sqrt(float x)
+{
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
 constexpr int EPI_PITCH = 36;
 constexpr int EPI_SMEM = 4 * 32 * EPI_PITCH * 4;       // four epilogue warps
 
@@ -193,7 +211,7 @@ template <int NT, int ACTK, bool DBG = false>
 __device__ __forceinline__ void epilogue_warp(const TcParams &p, long long plane, int oy, int ox0, int n0, bool live, int wl, uint32_t taddr0,
                                               float *__restrict__ stage, const float *__restrict__ bias, const float *__restrict__ slope,
                                               const float *__restrict__ mul, const float *__restrict__ residual, float *__restrict__ y,
-                                              long long *t_ld = nullptr)
+                                              long long *t_ld = nullptr, int step_first = 0, int step_stride = 1)
 {
     const int lane = threadIdx.x & 31;
     const int nco = min(NT, p.Co - n0 * NT);       // multiple of 4
@@ -205,8 +223,31 @@ __device__ __forceinline__ void epilogue_warp(const TcParams &p, long long plane
     const long long arow = (((plane * p.aux_rows + oy + p.aux_y0) * (long long)p.aux_pitch) + ox0 + p.aux_x0) * p.Co + cbase + cch * 4;
     constexpr int STEP = NT >= 32 ? 32 : 16;
     constexpr int CCH = STEP / 4;                  // 16-byte chunks per pixel and step (8 or 4)
+    // the gate operand only ever accompanies a transcendental epilogue (sigmoid gate of the attention block, GDN / IGDN):
+    // the plain / PReLU instances do not carry its registers
+    constexpr bool CAN_MUL = ACTK != 0;
+    const bool has_mul = CAN_MUL && mul != nullptr;
+    // A layer whose epilogue reads a gate and / or a residual (GDN, attention gate, residual 1x1) is bound by these loads,
+    // not by the tensor pipe: with four warps issuing them AFTER the TMEM read the 1x1 layers ran at ~0.4 of the HBM floor
+    // (launch list profiles/r1y_*).  They are issued first - sixteen independent 128-bit loads per lane in flight while
+    // the accumulator chunk comes out of TMEM - and the single-CTA kernel runs two warps per lane quadrant, each taking
+    // every other 32-channel step (step_first / step_stride).
 #pragma unroll 1
-    for (int c0 = 0; c0 < NT; c0 += STEP) {
+    for (int c0 = step_first * STEP; c0 < NT; c0 += step_stride * STEP) {
+        const int co = c0 + cch * 4;
+        const bool mine = row_ok && cch < CCH && co < nco;
+        float4 m4[CAN_MUL ? 8 : 1], a4[8];
+        if (mine && (has_mul || residual)) {
+            const int xlim = min(wl, p.Wo) - ox0 - psub;      // pixel i of this lane is valid iff 4 i < xlim
+            const long long ao = arow + (long long)psub * p.Co + c0;
+            const int istep = 4 * p.Co;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const bool ok = live && 4 * i < xlim;
+                if (CAN_MUL) m4[i] = (has_mul && ok) ? __ldg(reinterpret_cast<const float4 *>(mul + ao + i * istep)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                a4[i] = (residual && ok) ? __ldg(reinterpret_cast<const float4 *>(residual + ao + i * istep)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
         if (live) {
             uint32_t v[STEP];
             const uint32_t taddr = taddr0 + (uint32_t)c0;
@@ -222,25 +263,10 @@ __device__ __forceinline__ void epilogue_warp(const TcParams &p, long long plane
                 *reinterpret_cast<float4 *>(sw + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
         }
         __syncwarp();
-        const int co = c0 + cch * 4;
-        if (row_ok && cch < CCH && co < nco) {
+        if (mine) {
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = b4;
             if (bias) b4 = *reinterpret_cast<const float4 *>(bias + cbase + co);
             if (p.act == 1) s4 = *reinterpret_cast<const float4 *>(slope + cbase + co);
-            // gate / residual operands of all eight pixels of this lane first: sixteen independent 128-bit loads in flight
-            // (issued one by one inside the loop they serialised two L2 round trips per pixel - the GDN / residual layers
-            // got slower, not faster, with the coalesced layout; profiles/r1k_*)
-            float4 m4[8], a4[8];
-            if (mul || residual) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int px = i * 4 + psub;
-                    const bool ok = live && ox0 + px < wl && ox0 + px < p.Wo;
-                    const long long ao = arow + (long long)px * p.Co + c0;
-                    m4[i] = (mul && ok) ? __ldg(reinterpret_cast<const float4 *>(mul + ao)) : make_float4(1.f, 1.f, 1.f, 1.f);
-                    a4[i] = (residual && ok) ? __ldg(reinterpret_cast<const float4 *>(residual + ao)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int px = i * 4 + psub;
@@ -256,18 +282,20 @@ __device__ __forceinline__ void epilogue_warp(const TcParams &p, long long plane
                             if (r.z < 0.f) r.z = __fmul_rn(r.z, s4.z);
                             if (r.w < 0.f) r.w = __fmul_rn(r.w, s4.w);
                         } else if (ACTK == 2) {     // sigmoid / rsqrt / sqrt live in separate kernel instances (ACTK = the act code):
-                            r.x = 1.0f / (1.0f + expf(-r.x)); r.y = 1.0f / (1.0f + expf(-r.y));      // inlined together they pushed the
-                            r.z = 1.0f / (1.0f + expf(-r.z)); r.w = 1.0f / (1.0f + expf(-r.w));      // kernels out of the instruction cache
+                            r.x = fast_sigmoid(r.x); r.y = fast_sigmoid(r.y);      // inlined together they pushed the kernels out of
+                            r.z = fast_sigmoid(r.z); r.w = fast_sigmoid(r.w);      // the instruction cache
                         } else if (ACTK == 3) {
-                            r.x = 1.0f / sqrtf(r.x); r.y = 1.0f / sqrtf(r.y); r.z = 1.0f / sqrtf(r.z); r.w = 1.0f / sqrtf(r.w);
+                            r.x = fast_rsqrt(r.x); r.y = fast_rsqrt(r.y); r.z = fast_rsqrt(r.z); r.w = fast_rsqrt(r.w);
                         } else if (ACTK == 4) {
-                            r.x = sqrtf(r.x); r.y = sqrtf(r.y); r.z = sqrtf(r.z); r.w = sqrtf(r.w);
+                            r.x = fast_sqrt(r.x); r.y = fast_sqrt(r.y); r.z = fast_sqrt(r.z); r.w = fast_sqrt(r.w);
                         }
-                        if (mul) { r.x = __fmul_rn(r.x, m4[i].x); r.y = __fmul_rn(r.y, m4[i].y); r.z = __fmul_rn(r.z, m4[i].z); r.w = __fmul_rn(r.w, m4[i].w); }
+                        if (CAN_MUL && has_mul) { r.x = __fmul_rn(r.x, m4[i].x); r.y = __fmul_rn(r.y, m4[i].y); r.z = __fmul_rn(r.z, m4[i].z); r.w = __fmul_rn(r.w, m4[i].w); }
                         if (residual) { r.x = __fadd_rn(a4[i].x, r.x); r.y = __fadd_rn(a4[i].y, r.y); r.z = __fadd_rn(a4[i].z, r.z); r.w = __fadd_rn(a4[i].w, r.w); }
                     }
                     *reinterpret_cast<float4 *>(yrow + (long long)px * p.Co + c0) = r;
                 }
+                // the gated instances hold 64 operand registers: keep the compiler from batching all eight pixels' LDS
+                if (CAN_MUL && (i & 1)) asm volatile("" ::: "memory");
             }
         }
         __syncwarp();
@@ -275,7 +303,7 @@ __device__ __forceinline__ void epilogue_warp(const TcParams &p, long long plane
 }
 
 template <int NT, int ACTK>
-__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap map_x,
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                   const __grid_constant__ CUtensorMap map_w, TcParams p,
                                                                   const float *__restrict__ bias, const float *__restrict__ slope,
                                                                   const float *__restrict__ mul, const float *__restrict__ residual,
@@ -308,7 +336,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], 4);           // one arrival per epilogue warp
+            mbar_init(&acc_empty[s], 8);           // one arrival per epilogue warp
         }
         mbar_fence_init();
     }
@@ -386,7 +414,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     } else {
         // ===================================================================================== epilogue warps
         const int q = warp & 3;                 // TMEM lane quadrant this warp may read
-        const int m = q * 32 + lane;            // pixel of the tile owned by this thread
+        const int half = (warp - 2) >> 2;       // warps 2..5 take the even 32-channel steps of a tile, warps 6..9 the odd ones
         int acc = 0;
         uint32_t acc_phase = 0;
         for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -402,7 +430,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 tc_fence_after();
             }
             epilogue_warp<NT, ACTK>(p, tl.plane, oy, ox0, tl.n0, live, wl, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT),
-                                     s_stage + q * 32 * EPI_PITCH, bias ? s_bias : nullptr, s_slope, mul, residual, y);
+                                     s_stage + (warp - 2) * 32 * EPI_PITCH, bias ? s_bias : nullptr, s_slope, mul, residual, y, nullptr, half, 2);
             if (live) {
                 tc_fence_before();
                 __syncwarp();
@@ -808,7 +836,7 @@ static int launch_tc_v(const CUtensorMap &mx, const CUtensorMap &mw, const TcPar
         attr = true;
     }
     long long grid = p.total_tiles < pcx_sm_count() ? p.total_tiles : pcx_sm_count();
-    conv_tc_kernel<NT, ACTK><<<(unsigned)grid, NUM_THREADS, C::SMEM, s>>>(mx, mw, p, bias, slope, mul, residual, y);
+    conv_tc_kernel<NT, ACTK><<<(unsigned)grid, TC_THREADS, C::SMEM, s>>>(mx, mw, p, bias, slope, mul, residual, y);
     PCX_LAUNCHED();
     return PCX_OK;
 }
@@ -846,7 +874,8 @@ static int launch_tc(const CUtensorMap &mx, const CUtensorMap &mw, const TcParam
     case 2: return launch_tc_v<NT, 2>(mx, mw, p, bias, slope, mul, residual, y, s);
     case 3: return launch_tc_v<NT, 3>(mx, mw, p, bias, slope, mul, residual, y, s);
     case 4: return launch_tc_v<NT, 4>(mx, mw, p, bias, slope, mul, residual, y, s);
-    default: return launch_tc_v<NT, 0>(mx, mw, p, bias, slope, mul, residual, y, s);
+    default:    // ACTK 5 = plain / PReLU epilogue that also carries a gate operand (not used by the codec's layers)
+        return mul ? launch_tc_v<NT, 5>(mx, mw, p, bias, slope, mul, residual, y, s) : launch_tc_v<NT, 0>(mx, mw, p, bias, slope, mul, residual, y, s);
     }
 }
 template <int NT, bool DBG = false>
@@ -909,7 +938,7 @@ int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w,
         if (rc < 0) return (int)rc;
     }
 
-    const bool pair = pair_mode() != 0 && d.k == 3 && d.stride == 1 && d.Wo >= 64 && d.act <= 1;
+    const bool pair = pair_mode() != 0 && d.k == 3 && d.stride == 1 && d.Wo >= 64 && d.act <= 1 && d_mul == nullptr;
     const cuuint64_t plane_rows = (cuuint64_t)(d.in_plane_rows > 0 ? d.in_plane_rows : d.Hi);
 
     // ---- tensor maps
