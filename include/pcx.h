@@ -149,7 +149,12 @@ int pcx_dquant_fwd(const float *d_sym, const float *d_theta, float *d_centres, f
  *           (x [plane][Hi][in_pitch][Ci], y [plane][out_rows][out_pitch][Co], aux likewise), Ci % 32 == 0,
  *           Co <= 16 or Co % 96 == 0;
  *       1 = fp32 CUDA-core direct form on NCHW tensors (exact-order reference used to validate impl 0);
- *       2 = as 0, but d_w is already packed by pcx_conv_pack_weights (no per-call repack). */
+ *       2 = as 0, but d_w is already packed by pcx_conv_pack_weights (no per-call repack);
+ *       3 = as 2 with Dtow(stride 2, d2w) fused into the store (ResidualBlockUp / the decoder's last layer run
+ *           conv -> Dtow, model_zoo_v2.py:153-175, dtow_cuda.cu:38-55): d_w packed by pcx_conv_pack_weights_d2w,
+ *           y is [plane][out_rows][out_pitch][Co/4] and receives 2 Ho x 2 Wo pixels per plane at (out_y0, out_x0):
+ *           channel 4c + 2dy + dx of conv pixel (y,x) -> channel c of pixel (2y+dy, 2x+dx).  No d_mul / d_residual;
+ *           Co / 4 must be 96 or 192.  wl_out stays in conv-pixel units. */
 typedef struct pcx_conv_desc {
     int N, npart;            /* images, bands per image */
     int Ci, Hi, in_pitch;    /* input view: Hi rows of in_pitch pixels reachable from d_x */
@@ -171,6 +176,8 @@ int pcx_conv2d_fwd(const pcx_conv_desc *desc, const float *d_x, const float *d_w
 /* Repack OIHW fp32 weights into the tap-major layout the tensor-core kernel streams with TMA:
  * d_out [k*k][Co_pad][Ci_pad]. Returns the element count needed when d_out == NULL. */
 long long pcx_conv_pack_weights(const float *d_w, float *d_out, int Co, int Ci, int k, void *stream);
+/* Same layout with the output channels permuted for impl 3 (GEMM column q * Co/4 + c <- channel 4c + q). */
+long long pcx_conv_pack_weights_d2w(const float *d_w, float *d_out, int Co, int Ci, int k, void *stream);
 /* PseudoGDNV2.forward (PCONV_operator/PseudoContextV2.py:186-216): y = x / sqrt(beta' + gamma' x^2)
  * (inverse: x * sqrt(..)), invalid columns -> 0.  beta'/gamma' are the reparametrised values computed by
  * pcx_gdn_params from the raw parameters (LowerBound, GDN.py:6-22). */

@@ -71,6 +71,7 @@ PROTOTYPES = {
     "pcx_dquant_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _IP, _P]),
     "pcx_conv2d_fwd": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
     "pcx_conv_pack_weights": (C.c_longlong, [_P, _P, _I, _I, _I, _P]),
+    "pcx_conv_pack_weights_d2w": (C.c_longlong, [_P, _P, _I, _I, _I, _P]),
     "pcx_gdn_params": (_I, [_P, _P, _P, _P, _I, _F, _F, _P]),
     "pcx_gdn_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _IP, _I, _P]),
     "pcx_ctx_order": (_I, [_IP, _I, _I, _I, _IP, _IP]),

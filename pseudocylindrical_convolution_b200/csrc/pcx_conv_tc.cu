@@ -38,6 +38,7 @@ struct TcParams {
     int out_rows, out_pitch, out_y0, out_x0;
     int aux_rows, aux_pitch, aux_y0, aux_x0;
     int k, stride, act;
+    int d2w;                // 1: write the result depth-to-space (Dtow stride 2 fused into the store), GEMM column q*Co/4 + c = channel 4c + q
     int bw, bh;             // tile = bw columns x bh rows, bw * bh = 128
     int tiles_x, tiles_y, n_tiles, co_pad;
     long long total_tiles;
@@ -149,11 +150,13 @@ __host__ __device__ constexpr uint32_t instr_desc(int n)
     return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
-__device__ __forceinline__ void stage_channel_vectors(float *s_bias, float *s_slope, const float *bias, const float *slope, int Co)
+__device__ __forceinline__ void stage_channel_vectors(float *s_bias, float *s_slope, const float *bias, const float *slope, int Co, int d2w)
 {
+    const int cq = Co >> 2;
     for (int i = threadIdx.x; i < MAX_CO_STAGED; i += blockDim.x) {
-        s_bias[i] = (bias != nullptr && i < Co) ? bias[i] : 0.f;
-        s_slope[i] = (slope != nullptr && i < Co) ? slope[i] : 1.f;
+        const int src = (d2w && i < Co) ? 4 * (i % cq) + i / cq : i;       // GEMM column -> the layer's channel index
+        s_bias[i] = (bias != nullptr && i < Co) ? bias[src] : 0.f;
+        s_slope[i] = (slope != nullptr && i < Co) ? slope[src] : 1.f;
     }
 }
 
@@ -204,10 +207,25 @@ __device__ __forceinline__ float fast_sqrt(float x)
 }
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
+// The epilogue's transpose tile is addressed through explicit shared-state-space instructions: the kernels derive their
+// shared-memory pointers from an integer-aligned base, so plain dereferences compile to GENERIC LD / ST, which the compiler
+// must keep ordered against the global stores of the previous pixel - the per-pixel LDS -> SFU -> STG chains ran one
+// after the other (SASS of r2a) and the few warps of the CTA could not hide their latency.
+__device__ __forceinline__ float4 lds_f4(uint32_t a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t a, float x, float y, float z, float w)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w));
+}
+
 constexpr int EPI_PITCH = 36;
 constexpr int EPI_SMEM = 4 * 32 * EPI_PITCH * 4;       // four epilogue warps
 
-template <int NT, int ACTK, bool DBG = false>
+template <int NT, int ACTK, bool DBG = false, bool PIPE = false>
 __device__ __forceinline__ void epilogue_warp(const TcParams &p, long long plane, int oy, int ox0, int n0, bool live, int wl, uint32_t taddr0,
                                               float *__restrict__ stage, const float *__restrict__ bias, const float *__restrict__ slope,
                                               const float *__restrict__ mul, const float *__restrict__ residual, float *__restrict__ y,
@@ -219,7 +237,11 @@ __device__ __forceinline__ void epilogue_warp(const TcParams &p, long long plane
     const bool row_ok = oy < p.Ho;
     // lane -> (pixel sub-index, 16-byte channel chunk) of the transposed view
     const int psub = lane >> 3, cch = lane & 7;
-    float *yrow = y + (((plane * p.out_rows + oy + p.out_y0) * (long long)p.out_pitch) + ox0 + p.out_x0) * p.Co + cbase + cch * 4;
+    // depth-to-space store (Dtow, dtow_cuda.cu:38-55, fused): the N tile n0 holds the channels 4c + n0 of the layer, i.e. output
+    // pixel (2 oy + n0 / 2, 2 ox + n0 % 2), channel c of a plane of Co / 4 channels - still whole 128-byte lines per store
+    const int ostride = p.d2w ? p.Co >> 1 : p.Co;          // floats between the stores of consecutive tile pixels
+    float *yrow = p.d2w ? y + (((plane * p.out_rows + 2 * oy + (n0 >> 1) + p.out_y0) * (long long)p.out_pitch) + 2 * ox0 + (n0 & 1) + p.out_x0) * (p.Co >> 2) + cch * 4
+                        : y + (((plane * p.out_rows + oy + p.out_y0) * (long long)p.out_pitch) + ox0 + p.out_x0) * p.Co + cbase + cch * 4;
     const long long arow = (((plane * p.aux_rows + oy + p.aux_y0) * (long long)p.aux_pitch) + ox0 + p.aux_x0) * p.Co + cbase + cch * 4;
     constexpr int STEP = NT >= 32 ? 32 : 16;
     constexpr int CCH = STEP / 4;                  // 16-byte chunks per pixel and step (8 or 4)
@@ -229,25 +251,37 @@ __device__ __forceinline__ void epilogue_warp(const TcParams &p, long long plane
     const bool has_mul = CAN_MUL && mul != nullptr;
     // A layer whose epilogue reads a gate and / or a residual (GDN, attention gate, residual 1x1) is bound by these loads,
     // not by the tensor pipe: with four warps issuing them AFTER the TMEM read the 1x1 layers ran at ~0.4 of the HBM floor
-    // (launch list profiles/r1y_*).  They are issued first - sixteen independent 128-bit loads per lane in flight while
-    // the accumulator chunk comes out of TMEM - and the single-CTA kernel runs two warps per lane quadrant, each taking
-    // every other 32-channel step (step_first / step_stride).
-#pragma unroll 1
-    for (int c0 = step_first * STEP; c0 < NT; c0 += step_stride * STEP) {
+    // and the warps stalled on the long scoreboard (launch list profiles/r1y_*, ncu profiles/r1z_conv_tc_gdn.json).
+    //   * the single-CTA kernel runs two warps per lane quadrant, each taking every other 32-channel step
+    //     (step_first / step_stride);
+    //   * the operand loads are software-pipelined by HALF steps: a lane's eight pixels form two groups of four; the next
+    //     step's loads of a group are issued as soon as the current step has consumed that group's registers, so 8..16
+    //     independent 128-bit loads per lane are in flight through the TMEM read, the transpose and the arithmetic.
+    const uint32_t stage_s = smem_u32(stage);
+    const int xlim = min(wl, p.Wo) - ox0 - psub;          // pixel i of this lane is valid iff 4 i < xlim
+    const int istep = 4 * p.Co;
+    const bool any_aux = has_mul || residual != nullptr;
+    float4 m4[CAN_MUL ? 8 : 1], a4[8];
+    auto load_aux = [&](int c0, int grp) {
         const int co = c0 + cch * 4;
-        const bool mine = row_ok && cch < CCH && co < nco;
-        float4 m4[CAN_MUL ? 8 : 1], a4[8];
-        if (mine && (has_mul || residual)) {
-            const int xlim = min(wl, p.Wo) - ox0 - psub;      // pixel i of this lane is valid iff 4 i < xlim
+        if (any_aux && row_ok && cch < CCH && co < nco) {
             const long long ao = arow + (long long)psub * p.Co + c0;
-            const int istep = 4 * p.Co;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
+            for (int k = 0; k < 4; k++) {
+                const int i = grp * 4 + k;
                 const bool ok = live && 4 * i < xlim;
                 if (CAN_MUL) m4[i] = (has_mul && ok) ? __ldg(reinterpret_cast<const float4 *>(mul + ao + i * istep)) : make_float4(1.f, 1.f, 1.f, 1.f);
                 a4[i] = (residual && ok) ? __ldg(reinterpret_cast<const float4 *>(residual + ao + i * istep)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
+    };
+    const int c_first = step_first * STEP, c_inc = step_stride * STEP;
+    if (PIPE && c_first < NT) { load_aux(c_first, 0); load_aux(c_first, 1); }
+#pragma unroll 1
+    for (int c0 = c_first; c0 < NT; c0 += c_inc) {
+        const int co = c0 + cch * 4;
+        const bool mine = row_ok && cch < CCH && co < nco;
+        if (!PIPE) { load_aux(c0, 0); load_aux(c0, 1); }     // CTA-pair kernel: tensor-bound, the plain order is the leaner one
         if (live) {
             uint32_t v[STEP];
             const uint32_t taddr = taddr0 + (uint32_t)c0;
@@ -257,46 +291,51 @@ __device__ __forceinline__ void epilogue_warp(const TcParams &p, long long plane
             else tmem_ld16(taddr, v);
             tmem_wait_ld();
             if (DBG) *t_ld += clock64() - t0;
-            float *sw = stage + lane * EPI_PITCH;
+            const uint32_t sw = stage_s + (uint32_t)(lane * EPI_PITCH * 4);
 #pragma unroll
             for (int j = 0; j < STEP; j += 4)
-                *reinterpret_cast<float4 *>(sw + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                sts_f4(sw + j * 4, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
         }
         __syncwarp();
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = b4;
         if (mine) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = b4;
             if (bias) b4 = *reinterpret_cast<const float4 *>(bias + cbase + co);
             if (p.act == 1) s4 = *reinterpret_cast<const float4 *>(slope + cbase + co);
+        }
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int px = i * 4 + psub;
-                const int ox = ox0 + px;
-                if (ox < p.Wo) {
-                    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (live && ox < wl) {
-                        r = *reinterpret_cast<const float4 *>(stage + px * EPI_PITCH + cch * 4);
-                        if (bias) { r.x = __fadd_rn(r.x, b4.x); r.y = __fadd_rn(r.y, b4.y); r.z = __fadd_rn(r.z, b4.z); r.w = __fadd_rn(r.w, b4.w); }
-                        if (p.act == 1) {
-                            if (r.x < 0.f) r.x = __fmul_rn(r.x, s4.x);
-                            if (r.y < 0.f) r.y = __fmul_rn(r.y, s4.y);
-                            if (r.z < 0.f) r.z = __fmul_rn(r.z, s4.z);
-                            if (r.w < 0.f) r.w = __fmul_rn(r.w, s4.w);
-                        } else if (ACTK == 2) {     // sigmoid / rsqrt / sqrt live in separate kernel instances (ACTK = the act code):
-                            r.x = fast_sigmoid(r.x); r.y = fast_sigmoid(r.y);      // inlined together they pushed the kernels out of
-                            r.z = fast_sigmoid(r.z); r.w = fast_sigmoid(r.w);      // the instruction cache
-                        } else if (ACTK == 3) {
-                            r.x = fast_rsqrt(r.x); r.y = fast_rsqrt(r.y); r.z = fast_rsqrt(r.z); r.w = fast_rsqrt(r.w);
-                        } else if (ACTK == 4) {
-                            r.x = fast_sqrt(r.x); r.y = fast_sqrt(r.y); r.z = fast_sqrt(r.z); r.w = fast_sqrt(r.w);
-                        }
-                        if (CAN_MUL && has_mul) { r.x = __fmul_rn(r.x, m4[i].x); r.y = __fmul_rn(r.y, m4[i].y); r.z = __fmul_rn(r.z, m4[i].z); r.w = __fmul_rn(r.w, m4[i].w); }
-                        if (residual) { r.x = __fadd_rn(a4[i].x, r.x); r.y = __fadd_rn(a4[i].y, r.y); r.z = __fadd_rn(a4[i].z, r.z); r.w = __fadd_rn(a4[i].w, r.w); }
+        for (int grp = 0; grp < 2; grp++) {
+            if (mine) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int i = grp * 4 + k;
+                    const int px = i * 4 + psub;
+                    const int ox = ox0 + px;
+                    // straight-line arithmetic on every pixel (invalid ones are zeroed by a select, out-of-row ones skip the
+                    // store): with branches around each pixel the compiler serialised the four LDS -> SFU -> STG chains and
+                    // the ten warps of the CTA could not hide their latency
+                    float4 r = lds_f4(stage_s + (uint32_t)((px * EPI_PITCH + cch * 4) * 4));
+                    if (bias) { r.x = __fadd_rn(r.x, b4.x); r.y = __fadd_rn(r.y, b4.y); r.z = __fadd_rn(r.z, b4.z); r.w = __fadd_rn(r.w, b4.w); }
+                    if (p.act == 1) {
+                        r.x = r.x < 0.f ? __fmul_rn(r.x, s4.x) : r.x;
+                        r.y = r.y < 0.f ? __fmul_rn(r.y, s4.y) : r.y;
+                        r.z = r.z < 0.f ? __fmul_rn(r.z, s4.z) : r.z;
+                        r.w = r.w < 0.f ? __fmul_rn(r.w, s4.w) : r.w;
+                    } else if (ACTK == 2) {     // sigmoid / rsqrt / sqrt live in separate kernel instances (ACTK = the act code):
+                        r.x = fast_sigmoid(r.x); r.y = fast_sigmoid(r.y);      // inlined together they pushed the kernels out of
+                        r.z = fast_sigmoid(r.z); r.w = fast_sigmoid(r.w);      // the instruction cache
+                    } else if (ACTK == 3) {
+                        r.x = fast_rsqrt(r.x); r.y = fast_rsqrt(r.y); r.z = fast_rsqrt(r.z); r.w = fast_rsqrt(r.w);
+                    } else if (ACTK == 4) {
+                        r.x = fast_sqrt(r.x); r.y = fast_sqrt(r.y); r.z = fast_sqrt(r.z); r.w = fast_sqrt(r.w);
                     }
-                    *reinterpret_cast<float4 *>(yrow + (long long)px * p.Co + c0) = r;
+                    if (CAN_MUL && has_mul) { r.x = __fmul_rn(r.x, m4[i].x); r.y = __fmul_rn(r.y, m4[i].y); r.z = __fmul_rn(r.z, m4[i].z); r.w = __fmul_rn(r.w, m4[i].w); }
+                    if (residual) { r.x = __fadd_rn(a4[i].x, r.x); r.y = __fadd_rn(a4[i].y, r.y); r.z = __fadd_rn(a4[i].z, r.z); r.w = __fadd_rn(a4[i].w, r.w); }
+                    if (!(live && ox < wl)) r = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ox < p.Wo) *reinterpret_cast<float4 *>(yrow + (long long)px * ostride + c0) = r;
                 }
-                // the gated instances hold 64 operand registers: keep the compiler from batching all eight pixels' LDS
-                if (CAN_MUL && (i & 1)) asm volatile("" ::: "memory");
             }
+            // this group's operand registers are free: the next step's loads go out now
+            if (PIPE && c0 + c_inc < NT) load_aux(c0 + c_inc, grp);
         }
         __syncwarp();
     }
@@ -322,7 +361,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     float *s_bias = reinterpret_cast<float *>(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256);
     float *s_slope = s_bias + MAX_CO_STAGED;
     float *s_stage = s_slope + MAX_CO_STAGED;
-    stage_channel_vectors(s_bias, s_slope, bias, slope, p.Co);
+    stage_channel_vectors(s_bias, s_slope, bias, slope, p.Co, p.d2w);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -429,7 +468,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 mbar_wait(&acc_full[acc], acc_phase);
                 tc_fence_after();
             }
-            epilogue_warp<NT, ACTK>(p, tl.plane, oy, ox0, tl.n0, live, wl, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT),
+            epilogue_warp<NT, ACTK, false, true>(p, tl.plane, oy, ox0, tl.n0, live, wl, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT),
                                      s_stage + (warp - 2) * 32 * EPI_PITCH, bias ? s_bias : nullptr, s_slope, mul, residual, y, nullptr, half, 2);
             if (live) {
                 tc_fence_before();
@@ -603,7 +642,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     float *s_bias = reinterpret_cast<float *>(b_base + (size_t)B2_STAGES * C::B_STAGE + 512);
     float *s_slope = s_bias + MAX_CO_STAGED;
     float *s_stage = s_slope + MAX_CO_STAGED;
-    stage_channel_vectors(s_bias, s_slope, bias, slope, p.Co);
+    stage_channel_vectors(s_bias, s_slope, bias, slope, p.Co, p.d2w);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -756,7 +795,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 }
 
 // OIHW fp32 -> [tap][Co_pad][Ci], values rounded to the nearest TF32 (the MMA would otherwise truncate them)
-__global__ void pack_weights_kernel(const float *__restrict__ w, float *__restrict__ out, int Co, int Ci, int kk, int co_pad)
+__global__ void pack_weights_kernel(const float *__restrict__ w, float *__restrict__ out, int Co, int Ci, int kk, int co_pad, int d2w)
 {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)kk * co_pad * Ci;
@@ -766,7 +805,8 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, float *__restri
     int tap = (int)(idx / Ci / co_pad);
     float v = 0.f;
     if (co < Co) {
-        v = w[((long long)co * Ci + ci) * kk + tap];
+        const int cs = d2w ? 4 * (co % (Co >> 2)) + co / (Co >> 2) : co;      // depth-to-space column order (see TcParams::d2w)
+        v = w[((long long)cs * Ci + ci) * kk + tap];
         uint32_t r;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
         v = __uint_as_float(r);
@@ -809,7 +849,23 @@ static std::mutex g_pack_mutex;
 static PackedWeights g_pack_cache[512];
 static int g_pack_next = 0;
 
+static long long pack_weights(const float *d_w, float *d_out, int Co, int Ci, int k, int d2w, void *stream);
+
 extern "C" long long pcx_conv_pack_weights(const float *d_w, float *d_out, int Co, int Ci, int k, void *stream)
+{
+    return pack_weights(d_w, d_out, Co, Ci, k, 0, stream);
+}
+
+extern "C" long long pcx_conv_pack_weights_d2w(const float *d_w, float *d_out, int Co, int Ci, int k, void *stream)
+{
+    if (Co % 4 != 0 || n_tile_for(Co) != Co / 4) {
+        pcx_set_error("fused depth-to-space needs Co / 4 to be one N tile (96 or 192 channels), got Co=%d", Co);
+        return PCX_EINVAL;
+    }
+    return pack_weights(d_w, d_out, Co, Ci, k, 1, stream);
+}
+
+static long long pack_weights(const float *d_w, float *d_out, int Co, int Ci, int k, int d2w, void *stream)
 {
     int nt = n_tile_for(Co);
     if (nt == 0 || Ci % BLOCK_K != 0 || (k != 1 && k != 3)) {
@@ -820,7 +876,7 @@ extern "C" long long pcx_conv_pack_weights(const float *d_w, float *d_out, int C
     long long total = (long long)k * k * co_pad * Ci;
     if (d_out == nullptr) return total;
     if (d_w == nullptr) { pcx_set_error("null weights"); return PCX_EINVAL; }
-    pack_weights_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(d_w, d_out, Co, Ci, k * k, co_pad);
+    pack_weights_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(d_w, d_out, Co, Ci, k * k, co_pad, d2w);
     PCX_LAUNCHED();
     return total;
 }
@@ -916,7 +972,8 @@ int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w,
     //      tensor may have been updated in place; the repack is <= 5 MB)
     const int co_pad = (d.Co + nt - 1) / nt * nt;
     float *packed = nullptr;
-    if (d.impl == 2) {
+    PCX_REQUIRE(d.impl != 3 || (d.Co % 4 == 0 && nt == d.Co / 4), "fused depth-to-space needs Co / 4 to be one N tile (96 or 192 channels), got Co=%d", d.Co);
+    if (d.impl == 2 || d.impl == 3) {
         PCX_REQUIRE((reinterpret_cast<uintptr_t>(d_w) & 15) == 0, "packed weights must be 16-byte aligned");
         packed = const_cast<float *>(d_w);
     } else {
@@ -981,6 +1038,7 @@ int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w,
     p.out_rows = d.out_rows; p.out_pitch = d.out_pitch; p.out_y0 = d.out_y0; p.out_x0 = d.out_x0;
     p.aux_rows = d.aux_rows; p.aux_pitch = d.aux_pitch; p.aux_y0 = d.aux_y0; p.aux_x0 = d.aux_x0;
     p.k = d.k; p.stride = d.stride; p.act = d.act;
+    p.d2w = d.impl == 3 ? 1 : 0;
     p.bw = bw; p.bh = bh;
     p.tiles_x = (d.Wo + bw - 1) / bw;
     p.tiles_y = (d.Ho + bh - 1) / bh;

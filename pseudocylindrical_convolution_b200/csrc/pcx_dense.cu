@@ -210,14 +210,16 @@ int pcx_conv2d_fwd(const pcx_conv_desc *desc, const float *d_x, const float *d_w
     PCX_REQUIRE(d.Ci > 0 && d.Co > 0 && d.Ho > 0 && d.Wo > 0, "bad extent");
     PCX_REQUIRE((d.Ho - 1) * d.stride + d.k <= d.Hi, "output rows %d read past the %d input rows", d.Ho, d.Hi);
     PCX_REQUIRE((d.Wo - 1) * d.stride + d.k <= d.in_pitch, "output columns %d read past the input pitch %d", d.Wo, d.in_pitch);
-    PCX_REQUIRE(d.out_y0 >= 0 && d.out_x0 >= 0 && d.out_y0 + d.Ho <= d.out_rows && d.out_x0 + d.Wo <= d.out_pitch, "output window outside the output plane");
+    const int up = d.impl == 3 ? 2 : 1;      // impl 3 writes the result depth-to-space (2 Ho x 2 Wo pixels of Co / 4 channels)
+    PCX_REQUIRE(d.out_y0 >= 0 && d.out_x0 >= 0 && d.out_y0 + up * d.Ho <= d.out_rows && d.out_x0 + up * d.Wo <= d.out_pitch, "output window outside the output plane");
+    PCX_REQUIRE(d.impl != 3 || (d.Co % 4 == 0 && !d_mul && !d_residual), "impl 3 (fused depth-to-space) needs Co %% 4 == 0 and no gate / residual operand");
     PCX_REQUIRE(d.act >= 0 && d.act <= 4, "act %d", d.act);
     PCX_REQUIRE(d.act <= 2 || d.impl != 1, "act %d (rsqrt / sqrt) is implemented by the tensor-core path only", d.act);
     PCX_REQUIRE(d.in_plane_rows == 0 || (d.in_plane_rows >= d.Hi && d.impl != 1), "in_plane_rows %d (tensor-core path only, >= Hi)", d.in_plane_rows);
     PCX_REQUIRE(d.act != 1 || d_slope, "PReLU needs slopes");
     if (d_mul || d_residual)
         PCX_REQUIRE(d.aux_y0 >= 0 && d.aux_x0 >= 0 && d.aux_y0 + d.Ho <= d.aux_rows && d.aux_x0 + d.Wo <= d.aux_pitch, "aux window outside the aux plane");
-    if (d.impl == 0 || d.impl == 2) return pcx_conv2d_tc(desc, d_x, d_w, d_bias, d_slope, d_mul, d_residual, d_y, stream);
+    if (d.impl == 0 || d.impl == 2 || d.impl == 3) return pcx_conv2d_tc(desc, d_x, d_w, d_bias, d_slope, d_mul, d_residual, d_y, stream);
     PCX_REQUIRE(d.impl == 1, "impl %d", d.impl);
     ConvGeom G;
     G.d = d;

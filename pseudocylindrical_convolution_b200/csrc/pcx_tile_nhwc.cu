@@ -41,6 +41,11 @@ __device__ __forceinline__ void cp_async4(float *dst_smem, const float *src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(float *dst_smem, const float *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+
 __device__ __forceinline__ void cp_async_wait_all()
 {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
@@ -441,6 +446,141 @@ __global__ void __launch_bounds__(SP_THREADS, 2) slice_pad_tma_kernel(const floa
     }
 }
 
+// ------------------------------------------------------------------------------------------------ slice + pad, third version
+// The TMA version above tops out at 0.67-0.70 of the HBM rate with nothing saturated (ncu r1g: 47 % SM throughput, 28 %
+// warps active): every iteration is wait -> compute with lanes along x -> bar.sync -> store with lanes along channels, and
+// in the narrow polar bands six of its eight consumer warps idle.  This version follows the structure that took the uslice
+// gather to 0.88:
+//   * one CTA per super-tile (tile row, band, column chunk), 4 CTAs / SM, looping over (image, 32-channel chunk) with
+//     double-buffered 16-byte cp.async staging of the circular ERP span (rows 16-byte aligned, like the TMA rows);
+//   * a lane owns FOUR CONSECUTIVE CHANNELS of a pixel (lane = 4 pixels x 8 channel quads), so the resampled values leave
+//     as one 128-bit channels-last store per pixel - four full 128-byte lines per warp instruction - with NO second pass
+//     through shared memory; the channel rows are skewed by 4 floats per channel quad, which makes the 4-byte tap loads
+//     of a warp (8 quads x 4 consecutive columns) hit 32 different banks;
+//   * per-pixel recipes (tap offsets, cubic weights, halo weight) are built once per CTA in shared memory.
+// Same expression shapes (tap4_ref<true>, lerp2_ref) -> bit-identical tiles.
+constexpr int S3_PITCH = 192;                 // floats per staged channel row: SROW (160) + the largest skew (28), = 0 mod 8
+constexpr int S3_BUF = CB * S3_PITCH;         // floats per staging buffer (24 KB)
+constexpr int S3_THREADS = 256;
+
+__device__ __forceinline__ int s3_row(int c) { return c * S3_PITCH + (((c >> 2) & 7) << 2); }
+
+__global__ void __launch_bounds__(S3_THREADS, 4) slice_pad_v3_kernel(const float *__restrict__ erp, float *__restrict__ out,
+                                                                   const int *__restrict__ stab, const float4 *__restrict__ swt,
+                                                                   const int *__restrict__ hband, const int *__restrict__ hrow,
+                                                                   const int *__restrict__ hcol, const float *__restrict__ htw,
+                                                                   Bands bands, SlicePadParams P)
+{
+    extern __shared__ __align__(128) unsigned char s3_smem[];
+    float *s_in = reinterpret_cast<float *>(s3_smem);                               // [2][CB][S3_PITCH]
+    ColRecipe *rec = reinterpret_cast<ColRecipe *>(s3_smem + 2 * S3_BUF * 4);       // [XB_MAX]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int npart = bands.npart;
+    const int W = P.W, h = P.h, pad = P.pad, C = P.C;
+    const int OH = h + 2 * pad;
+
+    const SuperGeom G = super_geometry(blockIdx.x, bands, P, stab, hband, hrow, hcol);
+    const int nx = G.x1 - G.x0;
+    const int n2 = G.span_al - G.n1;
+
+    // ---- per-column recipes (tap offsets relative to the aligned span base)
+    if (threadIdx.x < nx) {
+        const int *tab = stab + (i64)G.sb * W;
+        const float4 *wtab = swt + (i64)G.sb * W;
+        const int x = G.x0 + threadIdx.x;
+        ColRecipe r;
+        if (G.hr < 0) {
+            r.wa = wtab[x];
+            const int o = tab[x] - 1 - G.base_al;
+            r.oa = o < 0 ? o + W : o;
+            r.wb = r.wa; r.ob = r.oa; r.t = 0.f;
+        } else {
+            const i64 e = (i64)G.hr * W + x;
+            const int q = hcol[e];
+            const int q1 = (q + 1 == G.wsrc) ? 0 : q + 1;
+            r.wa = wtab[q];
+            r.wb = wtab[q1];
+            int o = tab[q] - 1 - G.base_al;
+            r.oa = o < 0 ? o + W : o;
+            o = tab[q1] - 1 - G.base_al;
+            r.ob = o < 0 ? o + W : o;
+            r.t = htw[e];
+        }
+        r.pad_ = 0;
+        rec[threadIdx.x] = r;
+    }
+
+    // ---- staging: thread -> (channel row = tid / 8, 16-byte chunks tid % 8, +8, ...)
+    const int sc = threadIdx.x >> 3, sq = threadIdx.x & 7;
+    const int span4 = G.span_al >> 2, n14 = G.n1 >> 2;
+    const i64 cstride = (i64)h * npart * W;
+    const int iters = P.N * P.cchunks;
+    auto stage = [&](int it, float *buf) {
+        const int n = it / P.cchunks, c0 = (it - n * P.cchunks) * CB;
+        if (sc < min(CB, C - c0)) {
+            const float *sr = erp + (((i64)n * C + c0 + sc) * (i64)(h * npart) + G.erow) * W;
+            float *dr = buf + s3_row(sc);
+            for (int j = sq; j < span4; j += 8)
+                cp_async16(dr + 4 * j, j < n14 ? sr + G.base_al + 4 * j : sr + 4 * (j - n14));
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(0, s_in);
+
+    const int xsub = lane >> 3, cq = lane & 7;
+    const int crow = s3_row(cq * 4);              // this lane's four channel rows: crow + m * S3_PITCH
+    for (int it = 0; it < iters; it++) {
+        const float *buf = s_in + (it & 1) * S3_BUF;
+        if (it + 1 < iters) {
+            stage(it + 1, s_in + ((it + 1) & 1) * S3_BUF);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();                           // staged data (and, the first time, the recipes) visible
+        const int n = it / P.cchunks, c0 = (it - n * P.cchunks) * CB;
+        const int c = c0 + cq * 4;
+        if (c < C) {                               // C % 4 == 0: a lane's four channels are all valid or all not
+            float *orow = out + ((((i64)n * npart + G.g) * OH + G.y) * (i64)P.out_pitch) * C + c;
+            const float *mine = buf + crow;
+            for (int xi = xsub + 4 * warp; xi < nx; xi += 32) {
+                const ColRecipe r = rec[xi];
+                float4 v;
+                {
+                    const float *t0 = mine + r.oa;
+                    v.x = tap4_ref<true>(r.wa, t0[0], t0[1], t0[2], t0[3]);
+                    v.y = tap4_ref<true>(r.wa, t0[S3_PITCH], t0[S3_PITCH + 1], t0[S3_PITCH + 2], t0[S3_PITCH + 3]);
+                    v.z = tap4_ref<true>(r.wa, t0[2 * S3_PITCH], t0[2 * S3_PITCH + 1], t0[2 * S3_PITCH + 2], t0[2 * S3_PITCH + 3]);
+                    v.w = tap4_ref<true>(r.wa, t0[3 * S3_PITCH], t0[3 * S3_PITCH + 1], t0[3 * S3_PITCH + 2], t0[3 * S3_PITCH + 3]);
+                }
+                if (G.hr >= 0) {
+                    const float *t1 = mine + r.ob;
+                    const float bx = tap4_ref<true>(r.wb, t1[0], t1[1], t1[2], t1[3]);
+                    const float by = tap4_ref<true>(r.wb, t1[S3_PITCH], t1[S3_PITCH + 1], t1[S3_PITCH + 2], t1[S3_PITCH + 3]);
+                    const float bz = tap4_ref<true>(r.wb, t1[2 * S3_PITCH], t1[2 * S3_PITCH + 1], t1[2 * S3_PITCH + 2], t1[2 * S3_PITCH + 3]);
+                    const float bw = tap4_ref<true>(r.wb, t1[3 * S3_PITCH], t1[3 * S3_PITCH + 1], t1[3 * S3_PITCH + 2], t1[3 * S3_PITCH + 3]);
+                    v.x = lerp2_ref(v.x, bx, r.t); v.y = lerp2_ref(v.y, by, r.t);
+                    v.z = lerp2_ref(v.z, bz, r.t); v.w = lerp2_ref(v.w, bw, r.t);
+                }
+                const int x = G.x0 + xi;
+                *reinterpret_cast<float4 *>(orow + (i64)(pad + x) * C) = v;
+                // longitude wrap (pseudo_pad.cu:82-96): left pad <- last `pad` columns, right pad <- first `pad` columns
+                if (x < pad) *reinterpret_cast<float4 *>(orow + (i64)(pad + G.wl + x) * C) = v;
+                if (x >= G.wl - pad) *reinterpret_cast<float4 *>(orow + (i64)(x - (G.wl - pad)) * C) = v;
+            }
+            if (P.zero_invalid) {
+                // columns beyond the band (PseudoPad leaves them 0; pseudo_pad.cu:39-54), split over the row's chunks
+                const int chunks = (G.wl + P.xb[G.g] - 1) / P.xb[G.g];
+                const int zb = (P.out_pitch - G.wl - 2 * pad + chunks - 1) / chunks;
+                const int X0 = G.wl + 2 * pad + (G.x0 / P.xb[G.g]) * zb, X1 = min(X0 + zb, P.out_pitch);
+                for (int X = X0 + xsub + 4 * warp; X < X1; X += 32)
+                    *reinterpret_cast<float4 *>(orow + (i64)X * C) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        __syncthreads();                           // everyone is done with this buffer before it is restaged
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ uslice
 struct UsliceParams {
     int N, C, h, W;
@@ -535,11 +675,6 @@ __global__ void __launch_bounds__(NTHREADS) uslice_nhwc_kernel(const float *__re
 //     resampled and the six 128-byte pieces of a 768-byte tile pixel are fetched back to back (DRAM page locality).
 // ~6.5 thread-instructions per output element instead of ~11; bit-identical results (same tap4_ref expression).
 constexpr int U2_ROWS = UXB + 8 + 4;          // staged source columns per buffer: scap (136) + 3 taps, rounded up
-
-__device__ __forceinline__ void cp_async16(float *dst_smem, const float *src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
 
 __global__ void __launch_bounds__(NTHREADS) uslice_nhwc_v2_kernel(const float *__restrict__ tiles, float *__restrict__ erp,
                                                                   const int *__restrict__ utab, const float4 *__restrict__ uwt,
@@ -675,11 +810,26 @@ int pcx_slice_pad_nhwc(const float *d_in, float *d_out, int N, int C, int H, int
     PCX_REQUIRE((i64)P.cchunks * (P.h + 2 * pad) <= 65535 && (i64)N * npart <= 65535, "grid too large");
     const dim3 grid(P.xchunks, P.cchunks * (P.h + 2 * pad), N * npart);
     const size_t smem = XB_MAX * sizeof(ColRecipe) + (size_t)CB * ((P.scap + 3) | 1) * sizeof(float);
-    static const bool force_v1 = getenv("PCX_SLICE_V1") != nullptr;
+    static const bool force_v1 = getenv("PCX_SLICE_V1") != nullptr || (getenv("PCX_SLICE_IMPL") && getenv("PCX_SLICE_IMPL")[0] == 'v');
     P.xoff[0] = 0;
     for (int i = 0; i < PCX_MAX_PART; i++) P.xoff[i + 1] = P.xoff[i] + (i < npart ? (wl[i] + P.xb[i] - 1) / P.xb[i] : 0);
     P.xtotal = P.xoff[npart];
-    if (W % 4 == 0 && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 && !force_v1) {
+    // PCX_SLICE_IMPL = tma | v1 forces one of the older kernels (A/B timing, tools/hbm_ops_bench.py)
+    static const char *impl_env = getenv("PCX_SLICE_IMPL");
+    static const bool force_tma = impl_env && impl_env[0] == 't';
+    const bool aligned = W % 4 == 0 && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0;
+    if (aligned && C % 4 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && !force_v1 && !force_tma) {
+        constexpr int smem3 = 2 * S3_BUF * 4 + XB_MAX * (int)sizeof(ColRecipe);
+        static bool attr3 = false;
+        if (!attr3) {
+            PCX_CUDA(cudaFuncSetAttribute(slice_pad_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+            attr3 = true;
+        }
+        const i64 n_super = (i64)(P.h + 2 * pad) * P.xtotal;
+        PCX_REQUIRE(n_super < (1LL << 31), "grid too large");
+        slice_pad_v3_kernel<<<(unsigned)n_super, S3_THREADS, smem3, (cudaStream_t)stream>>>(d_in, d_out, d_src, (const float4 *)d_wt, d_band,
+                                                                                          d_row, d_col, d_tw, b, P);
+    } else if (aligned && !force_v1) {
         static bool attr = false;
         if (!attr) {
             PCX_CUDA(cudaFuncSetAttribute(slice_pad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM));

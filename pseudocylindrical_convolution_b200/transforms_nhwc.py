@@ -96,9 +96,10 @@ class Runner:
             self._problem = problem
 
     # ------------------------------------------------------------------------------------------ parameters
-    def packed(self, weight, ci_pad=None):
-        """OIHW parameter -> tap-major TF32 layout of the tensor-core kernels, cached until the parameter changes."""
-        key = id(weight)
+    def packed(self, weight, ci_pad=None, d2w=False):
+        """OIHW parameter -> tap-major TF32 layout of the tensor-core kernels, cached until the parameter changes.
+        d2w: output channels in the depth-to-space order of pcx_conv2d_fwd impl 3."""
+        key = (id(weight), d2w)
         ver = (weight.data_ptr(), weight._version, tuple(weight.shape), ci_pad)
         hit = self._packed.get(key)
         if hit is not None and hit[0] == ver:
@@ -113,9 +114,10 @@ class Runner:
             w, Ci = wp, ci_pad
         w = w.contiguous()
         s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        n = call("pcx_conv_pack_weights", None, None, Co, Ci, k, s)
+        fn = "pcx_conv_pack_weights_d2w" if d2w else "pcx_conv_pack_weights"
+        n = call(fn, None, None, Co, Ci, k, s)
         out = torch.empty(n, dtype=torch.float32, device=w.device)
-        call("pcx_conv_pack_weights", _p(w), _p(out), Co, Ci, k, s)
+        call(fn, _p(w), _p(out), Co, Ci, k, s)
         self._packed[key] = (ver, out)
         return out
 
@@ -124,15 +126,19 @@ class Runner:
 
     # ------------------------------------------------------------------------------------------ ops
     def conv(self, x: View, weight, bias, k, stride, Co, out: View, wl_out, act=ACT_NONE, slope=None, mul: View = None,
-             residual: View = None, ci_pad=None):
+             residual: View = None, ci_pad=None, d2w=False):
+        """d2w: Dtow(2) fused into the store - `out` is the (2 Ho, 2 Wo, Co / 4) view the pixel shuffle would produce."""
         Ho, Wo = (x.h - k) // stride + 1, (x.W - k) // stride + 1
-        assert (Ho, Wo) == (out.h, out.W) and out.C == Co, ((Ho, Wo), (out.h, out.W), out.C, Co)
+        if d2w:
+            assert (2 * Ho, 2 * Wo) == (out.h, out.W) and 4 * out.C == Co and mul is None and residual is None
+        else:
+            assert (Ho, Wo) == (out.h, out.W) and out.C == Co, ((Ho, Wo), (out.h, out.W), out.C, Co)
         d = ConvDesc()
         d.N, d.npart = x.planes // self.npart, self.npart
         d.Ci, d.Hi, d.in_pitch, d.in_plane_rows = x.C, x.rows - x.y0, x.pitch, x.rows
         d.Co, d.Ho, d.Wo = Co, Ho, Wo
         d.out_rows, d.out_pitch, d.out_y0, d.out_x0 = out.rows, out.pitch, out.y0, out.x0
-        d.k, d.stride, d.act, d.impl = k, stride, act, 2
+        d.k, d.stride, d.act, d.impl = k, stride, act, 3 if d2w else 2
         aux = mul if mul is not None else residual
         if aux is not None:
             if mul is not None and residual is not None:
@@ -143,16 +149,16 @@ class Runner:
             d.aux_rows, d.aux_pitch = Ho, Wo
         for g in range(self.npart):
             d.wl_out[g] = min(int(wl_out[g]), Wo)
-        call("pcx_conv2d_fwd", C.byref(d), x.ptr(), _p(self.packed(weight, ci_pad)), _p(bias), _p(slope),
+        call("pcx_conv2d_fwd", C.byref(d), x.ptr(), _p(self.packed(weight, ci_pad, d2w)), _p(bias), _p(slope),
              _p(mul.buf) if mul is not None else None, _p(residual.buf) if residual is not None else None, _p(out.buf),
              C.c_void_p(torch.cuda.current_stream().cuda_stream))
         return out
 
-    def conv_m(self, x, conv, out, wl_out, prelu=None, sigmoid=False, mul=None, residual=None, ci_pad=None):
+    def conv_m(self, x, conv, out, wl_out, prelu=None, sigmoid=False, mul=None, residual=None, ci_pad=None, d2w=False):
         """convolution described by an nn.Conv2d parameter container (+ optional nn.PReLU)"""
         act = ACT_PRELU if prelu is not None else (ACT_SIGMOID if sigmoid else ACT_NONE)
         return self.conv(x, conv.weight, conv.bias.data if conv.bias is not None else None, conv.kernel_size[0], conv.stride[0],
-                         conv.out_channels, out, wl_out, act, prelu.weight.data if prelu is not None else None, mul, residual, ci_pad)
+                         conv.out_channels, out, wl_out, act, prelu.weight.data if prelu is not None else None, mul, residual, ci_pad, d2w)
 
     def halo(self, a: View):
         """PseudoPadV2(2) of a padded activation, in place"""
@@ -240,13 +246,21 @@ def _residual_block_up(R: Runner, m, X: View):
     h2, W2 = 2 * X.h, 2 * X.W
     wl2 = R.widths(h2, W2)
     ch = X.C
-    b1 = R.conv_m(X.padded(1), m.conv1, R.plain(X.planes, X.h, X.W, 4 * ch), wl, prelu=m.relu1)
-    b1u = R.halo(R.dtow(b1, R.padded_act(X.planes, h2, W2, ch)))
-    R.release(b1)
+    fused = 4 * ch == m.conv1.out_channels and ch in (96, 192)      # Dtow folded into the convolutions' stores (impl 3)
+    if fused:
+        b1u = R.halo(R.conv_m(X.padded(1), m.conv1, R.padded_act(X.planes, h2, W2, ch), wl, prelu=m.relu1, d2w=True))
+    else:
+        b1 = R.conv_m(X.padded(1), m.conv1, R.plain(X.planes, X.h, X.W, 4 * ch), wl, prelu=m.relu1)
+        b1u = R.halo(R.dtow(b1, R.padded_act(X.planes, h2, W2, ch)))
+        R.release(b1)
     z = R.conv_m(b1u.padded(1), m.conv2, R.plain(X.planes, h2, W2, ch), wl2)
-    s = R.conv_m(X, m.short_cut, R.plain(X.planes, X.h, X.W, 4 * ch), wl)
-    su = R.dtow(s, R.plain(X.planes, h2, W2, ch))
-    R.release(s, b1u)
+    if fused:
+        su = R.conv_m(X, m.short_cut, R.plain(X.planes, h2, W2, ch), wl, d2w=True)
+    else:
+        s = R.conv_m(X, m.short_cut, R.plain(X.planes, X.h, X.W, 4 * ch), wl)
+        su = R.dtow(s, R.plain(X.planes, h2, W2, ch))
+        R.release(s)
+    R.release(b1u)
     out = R.gdn(m.relu2, z, su, R.padded_act(X.planes, h2, W2, ch), wl2)
     R.release(z, su)
     return R.halo(out)

@@ -483,3 +483,46 @@ def test_conv_tensor_core_vs_direct(cuda, orc, Ci, Co, k, s, act, h, W):
     scale = max(1.0, float(np.abs(mul).max())) if act != 2 else float(np.abs(mul).max())
     assert np.sqrt((err ** 2).mean()) < 1.5e-3, "rms err %g" % np.sqrt((err ** 2).mean())
     assert err.max() < 1e-2 * scale, "max err %g" % err.max()
+
+
+@pytest.mark.parametrize("k,h,W", [(3, 6, 256), (1, 5, 72), (3, 4, 640)])
+def test_conv_fused_depth_to_space(cuda, k, h, W):
+    """pcx_conv2d_fwd impl 3 (Dtow(2) folded into the store of a 192 -> 768 convolution: ResidualBlockUp conv1 / short_cut,
+    model_zoo_v2.py:153-175) must equal impl 2 followed by pcx_dtow_nhwc BIT FOR BIT - same MMAs, same epilogue arithmetic,
+    only the store addresses and the packed channel order differ.  CTA-pair kernel (k = 3) and single-CTA kernel (k = 1)."""
+    import ctypes as C
+    import torch
+    from pseudocylindrical_convolution_b200._lib import call
+    rng = np.random.default_rng(77)
+    Ci, Co, act = 192, 768, 1
+    halo = 2 if k == 3 else 0
+    Hi, Wi = h + halo, W + halo
+    wl = [max(4, W - 9 * (g % 4)) for g in range(16)]
+    wl[5] = min(W, 24)
+    x = torch.from_numpy(rng.standard_normal((16, Hi, Wi, Ci)).astype(np.float32)).to(cuda)
+    w = torch.from_numpy((rng.standard_normal((Co, Ci, k, k)) / np.sqrt(Ci * k * k)).astype(np.float32)).to(cuda)
+    b = torch.from_numpy(rng.standard_normal(Co).astype(np.float32)).to(cuda)
+    slope = torch.from_numpy((rng.random(Co) * 0.5).astype(np.float32)).to(cuda)
+    P = lambda t: C.c_void_p(t.data_ptr())
+
+    def packed(fn):
+        n = call(fn, None, None, Co, Ci, k, None)
+        out = torch.empty(n, dtype=torch.float32, device=cuda)
+        call(fn, P(w), P(out), Co, Ci, k, None)
+        return out
+
+    # two launches: conv into a plain tile, then the pixel shuffle into the interior of a padded plane
+    d, Ho, Wo = _conv_desc(16, Ci, Hi, Wi, Co, k, 1, act, wl, 2)
+    y = torch.empty((16, Ho, Wo, Co), device=cuda)
+    call("pcx_conv2d_fwd", C.byref(d), P(x), P(packed("pcx_conv_pack_weights")), P(b), P(slope), None, None, P(y), None)
+    rows, pitch, y0, x0 = 2 * Ho + 4, 2 * Wo + 5, 2, 3
+    ref = torch.full((16, rows, pitch, Co // 4), -7.0, device=cuda)
+    call("pcx_dtow_nhwc", P(y), P(ref), 16, Co // 4, Ho, Wo, Ho, Wo, 0, 0, rows, pitch, y0, x0, None)
+    # one launch
+    d, Ho, Wo = _conv_desc(16, Ci, Hi, Wi, Co, k, 1, act, wl, 3)
+    d.out_rows, d.out_pitch, d.out_y0, d.out_x0 = rows, pitch, y0, x0
+    got = torch.full((16, rows, pitch, Co // 4), -7.0, device=cuda)
+    call("pcx_conv2d_fwd", C.byref(d), P(x), P(packed("pcx_conv_pack_weights_d2w")), P(b), P(slope), None, None, P(got), None)
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref)
+    assert float(ref[:, y0:y0 + 2 * Ho, x0:x0 + 2 * Wo].abs().max()) > 0.1
