@@ -17,3 +17,6 @@ WAVE_IMPL = int(os.environ.get("PCX_WAVE_IMPL", "1"))
 WAVE_ENCODE_FULL = int(os.environ.get("PCX_WAVE_ENCODE_FULL", "1"))
 # rows (symbols) per image in one chunk of the one-shot encoder's CDF stream: the host codes chunk i while chunk i+1 is computed
 WAVE_CHUNK_ROWS = int(os.environ.get("PCX_WAVE_CHUNK_ROWS", str(1 << 17)))
+
+# capture the channels-last analysis / synthesis transforms into CUDA graphs (transforms_nhwc._run_graphed)
+CUDA_GRAPHS = True

@@ -676,7 +676,7 @@ __global__ void __launch_bounds__(NTHREADS) uslice_nhwc_kernel(const float *__re
 // ~6.5 thread-instructions per output element instead of ~11; bit-identical results (same tap4_ref expression).
 constexpr int U2_ROWS = UXB + 8 + 4;          // staged source columns per buffer: scap (136) + 3 taps, rounded up
 
-__global__ void __launch_bounds__(NTHREADS) uslice_nhwc_v2_kernel(const float *__restrict__ tiles, float *__restrict__ erp,
+__global__ void __launch_bounds__(NTHREADS, 4) uslice_nhwc_v2_kernel(const float *__restrict__ tiles, float *__restrict__ erp,
                                                                   const int *__restrict__ utab, const float4 *__restrict__ uwt,
                                                                   Bands bands, UsliceParams P)
 {

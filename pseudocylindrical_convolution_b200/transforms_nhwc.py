@@ -285,8 +285,57 @@ def _run_blocks(R, blocks, X, first_ci_pad=None):
     return X
 
 
-@torch.no_grad()
+# ---------------------------------------------------------------------------------------------------- CUDA graphs
+# A transform is ~100 launches; at 512x1024 (BASELINE configs[0]) each kernel runs for 5-20 us and the pass is bound by the
+# host issuing them through ctypes (2.4 ms for 102 launches, profiles/r1w_codec_bench.jsonl).  The second consecutive call
+# with the same (shape, device, parameter versions) captures the whole pass - our launches, the tensor-map encodes baked
+# into their parameters, and the few torch elementwise kernels - into one CUDA graph; later calls copy the input into the
+# graph's static buffer and replay it.  The graph is dropped as soon as the problem or any parameter changes (the Runner
+# recycles its tile buffers then), so a stale capture can never run.
+def _param_stamp(module):
+    return sum(int(p._version) for p in module.parameters()) + sum(int(b._version) for b in module.buffers())
+
+
+def _run_graphed(owner, fn, x):
+    from . import config
+    if not getattr(config, "CUDA_GRAPHS", True):
+        return fn(x)
+    st = owner.__dict__.setdefault("_pcx_graph", {"key": None, "seen": None, "graph": None, "failed": False})
+    key = (tuple(x.shape), x.device.index, x.data_ptr() % 16, _param_stamp(owner))
+    if st["graph"] is not None and st["key"] == key:
+        st["x"].copy_(x)
+        st["graph"].replay()
+        return st["y"].clone()
+    st["graph"] = st["x"] = st["y"] = st["key"] = None
+    y = fn(x)                                   # eager pass (also the warm-up of the capture below)
+    if st["seen"] == key and not st["failed"]:
+        try:
+            sx = x.clone()
+            torch.cuda.synchronize(x.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                sy = fn(sx)
+            st.update(graph=g, x=sx, y=sy, key=key)
+        except Exception as e:                  # capture is an optimisation: keep the eager path if the driver refuses
+            st["failed"] = True
+            import warnings
+            warnings.warn("pcx: CUDA-graph capture of the transform failed (%r); running eagerly" % (e,))
+    st["seen"] = key
+    return y
+
+
 def encoder_forward(enc, erp, slice_op):
+    """EncoderV2 + SphereSlice on an ERP batch; graph-replayed from the third call with the same problem (see above)."""
+    return _run_graphed(enc, lambda t: _encoder_forward(enc, t, slice_op), erp)
+
+
+def decoder_forward(dec, code, uslice_op):
+    """DecoderV2 + SphereUslice; graph-replayed from the third call with the same problem (see above)."""
+    return _run_graphed(dec, lambda t: _decoder_forward(dec, t, uslice_op), code)
+
+
+@torch.no_grad()
+def _encoder_forward(enc, erp, slice_op):
     """EncoderV2 (model_zoo_v2.py:129-151) on an ERP batch (N, 3, H, W) -> code (N*npart, code_channels, H/16/npart, W/16), NCHW."""
     R = enc._runner()
     R.reset(erp.device, tuple(erp.shape))
@@ -309,7 +358,7 @@ def encoder_forward(enc, erp, slice_op):
 
 
 @torch.no_grad()
-def decoder_forward(dec, code, uslice_op):
+def _decoder_forward(dec, code, uslice_op):
     """DecoderV2 (model_zoo_v2.py:189-211) + SphereUslice: code (N*npart, C, h, w) NCHW -> ERP (N, 3, 16 h npart, 16 w)."""
     R = dec._runner()
     R.reset(code.device, tuple(code.shape))

@@ -45,19 +45,21 @@ def main():
     for H, W, N in sizes:
         x = torch.from_numpy(smooth_images(1, 3, H, W, seed=1)).to(dev).repeat(N, 1, 1, 1).contiguous()
         n0 = lib.pcx_launch_count()
-        ms = timed(lambda: enc.latent(x), 1, 3)
-        launches = (lib.pcx_launch_count() - n0) // 4
+        ms = timed(lambda: enc.latent(x), 3, 5)        # call 2 of a new problem captures the CUDA graph: keep it out of the timing
+        launches = lib.pcx_launch_count() - n0            # launches issued by the host: 2 eager passes, then graph replays
         mp = N * H * W / 1e6
         # dense-grid FLOP counts of SURVEY.md 8d scaled to valid cells
         print(json.dumps({"stage": "analysis transform (TC)", "H": H, "W": W, "batch": N, "ms": ms, "MP/s": mp / ms * 1e3,
                           "TFLOP/s": 2 * 420552 * 0.8164 * mp * 1e6 / ms / 1e9, "launches": launches}))
         lat = enc.latent(x)
         sym = enc.dtw(enc.ext(enc.quant(lat)[1]))
-        ms = timed(lambda: dec.reconstruct(sym), 1, 3)
+        ms = timed(lambda: dec.reconstruct(sym), 3, 5)
         print(json.dumps({"stage": "synthesis transform (TC)", "H": H, "W": W, "batch": N, "ms": ms, "MP/s": mp / ms * 1e3,
                           "TFLOP/s": 2 * 517752 * 0.8164 * mp * 1e6 / ms / 1e9}))
         del lat, sym, x
         torch.cuda.empty_cache()
+    if "--transforms-only" in sys.argv:
+        return
     for H, W in ((512, 1024), (2048, 4096)):
         x = torch.from_numpy(smooth_images(1, 3, H, W, seed=1)).to(dev)
         path = os.path.join(d, "img.bin")
