@@ -19,6 +19,11 @@ namespace {
 
 struct Window { int first, count; };
 
+__device__ __forceinline__ void cp_async4_ctx(float *smem_dst, const float *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
 // planes [max(0, s-G+1), min(s+1, Hf+W-1)) of the wavefront order (entropy_conv_cuda_v2.cu:389-391)
 inline Window wave_window(const int *h_start, int psum, int G, int Hf, int W)
 {
@@ -199,7 +204,11 @@ struct CtCtx {
     int iw, tc, G, c6;
 };
 
-template <int GI, int I>
+// U = unroll factor of the channel-group loop, 0 = the compiler's choice.  The global-memory form needs the compiler's deep
+// unrolling (16 groups of loads in flight hide the L1 / L2 latency) although it makes the kernel ~750 KB of straight-line
+// code; the shared-memory form reads operands with ~30-cycle latency and is instead bound by instruction fetch at that
+// size, so it keeps the 75 chain loops compact (U = 2: one iteration's loads overlap the previous one's FMAs).
+template <int GI, int I, int U>
 __device__ __forceinline__ CtAcc ct_chain(const CtCtx &x)
 {
     CtAcc a = ct_zero();
@@ -209,7 +218,7 @@ __device__ __forceinline__ CtAcc ct_chain(const CtCtx &x)
         nk = nk > x.G ? x.G : nk;
         const float *ip = x.in_cell + (i64)m * x.chs + (kh - 2) * x.iw + (kw - 2);
         const float4 *wp = x.ws + m * 25 + kh * 5 + kw;
-        for (int k = 0; k < nk; k++) {
+        auto body = [&]() {
             const float4 w = *wp;
 #pragma unroll
             for (int c = 0; c < CT_CPT; c++) {
@@ -220,33 +229,101 @@ __device__ __forceinline__ CtAcc ct_chain(const CtCtx &x)
             }
             ip += (i64)GI * x.chs;
             wp += GI * 25;
+        };
+        if (U == 0) {
+            for (int k = 0; k < nk; k++) body();
+        } else {
+#pragma unroll U
+            for (int k = 0; k < nk; k++) body();
         }
     }
     return a;
 }
 
 // value of virtual lane T after the two shared-memory folds: ([T] + [T+64]) + ([T+32] + [T+96]); dead lanes hold +0.0f
-template <int GI, int T>
+template <int GI, int T, int U>
 __device__ __forceinline__ CtAcc ct_leaf(const CtCtx &x)
 {
-    CtAcc lo = ct_add(ct_chain<GI, T>(x), ct_chain<GI, T + 64>(x));
-    CtAcc hi = ct_add(ct_chain<GI, T + 32>(x), ct_zero());
+    CtAcc lo = ct_add(ct_chain<GI, T, U>(x), ct_chain<GI, T + 64, U>(x));
+    CtAcc hi = ct_add(ct_chain<GI, T + 32, U>(x), ct_zero());
     return ct_add(lo, hi);
 }
 // value of lane T after the shuffle-down steps 16 .. OFF
-template <int GI, int T, int OFF>
+template <int GI, int T, int OFF, int U = 0>
 struct CtTree {
     static __device__ __forceinline__ CtAcc run(const CtCtx &x)
     {
-        CtAcc a = CtTree<GI, T, OFF * 2>::run(x);
-        CtAcc b = CtTree<GI, T + OFF, OFF * 2>::run(x);
+        CtAcc a = CtTree<GI, T, OFF * 2, U>::run(x);
+        CtAcc b = CtTree<GI, T + OFF, OFF * 2, U>::run(x);
         return ct_add(a, b);
     }
 };
-template <int GI, int T>
-struct CtTree<GI, T, 32> {
-    static __device__ __forceinline__ CtAcc run(const CtCtx &x) { return ct_leaf<GI, T>(x); }
+template <int GI, int T, int U>
+struct CtTree<GI, T, 32, U> {
+    static __device__ __forceinline__ CtAcc run(const CtCtx &x) { return ct_leaf<GI, T, U>(x); }
 };
+
+// Runtime-loop form of the same tree for the shared-memory kernel: even with U = 1 the 75 template-expanded chain loops are
+// 81 KB of code and the kernel stays instruction-fetch-bound (1.00 ms per layer at 2048x4096 against 2.53 ms for the fully
+// unrolled 750 KB version - smaller was faster at every step).  Here the virtual lanes are walked by ONE loop in the tree's
+// depth-first leaf order T = bitrev5(i); a leaf is ([T] + [T+64]) + ([T+32] + 0) as before, and the shuffle-down levels
+// 16, 8, 4, 2, 1 are a binary-counter stack of five partial sums in named registers (level j combines when bit j of i is
+// set: earlier + later, the operand order of CtTree).  Same chains, same adds, same order - a few hundred instructions.
+template <int GI, int U>
+__device__ __forceinline__ CtAcc ct_chain_rt(const CtCtx &x, int I)
+{
+    CtAcc a = ct_zero();
+    if (I < 25 * GI) {
+        const int m = I / 25, r = I - m * 25, kh = r / 5, kw = r - kh * 5;
+        int nk = x.tc + 4 - kh - kw + x.c6;
+        nk = nk > x.G ? x.G : nk;
+        const int chs = (int)x.chs;
+        const float *ip = x.in_cell + m * chs + (kh - 2) * x.iw + (kw - 2);
+        const float4 *wp = x.ws + m * 25 + r;
+#pragma unroll U
+        for (int k = 0; k < nk; k++) {
+            const float4 w = *wp;
+#pragma unroll
+            for (int c = 0; c < CT_CPT; c++) {
+                const float v = ip[32 * c];
+                a.v[c][0] = __fmaf_rn(v, w.x, a.v[c][0]);
+                a.v[c][1] = __fmaf_rn(v, w.y, a.v[c][1]);
+                a.v[c][2] = __fmaf_rn(v, w.z, a.v[c][2]);
+            }
+            ip += GI * chs;
+            wp += GI * 25;
+        }
+    }
+    return a;
+}
+
+template <int GI, int U>
+__device__ __forceinline__ CtAcc ct_tree_rt(const CtCtx &x)
+{
+    CtAcc s0 = ct_zero(), s1 = ct_zero(), s2 = ct_zero(), s3 = ct_zero(), s4 = ct_zero(), acc = ct_zero();
+#pragma unroll 1
+    for (int i = 0; i < 32; i++) {
+        const int T = ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4);
+        const CtAcc lo = ct_add(ct_chain_rt<GI, U>(x, T), ct_chain_rt<GI, U>(x, T + 64));
+        const CtAcc hi = ct_add(ct_chain_rt<GI, U>(x, T + 32), ct_zero());
+        acc = ct_add(lo, hi);
+        if (i & 1) {
+            acc = ct_add(s0, acc);
+            if (i & 2) {
+                acc = ct_add(s1, acc);
+                if (i & 4) {
+                    acc = ct_add(s2, acc);
+                    if (i & 8) {
+                        acc = ct_add(s3, acc);
+                        if (i & 16) acc = ct_add(s4, acc);
+                        else s4 = acc;
+                    } else s3 = acc;
+                } else s2 = acc;
+            } else s1 = acc;
+        } else s0 = acc;
+    }
+    return acc;
+}
 
 template <int GI>
 __global__ void __launch_bounds__(32 * CT_WARPS, PCX_CT_MINB) ctx_conv_tiled_kernel(const float *__restrict__ in, const float *__restrict__ weight,
@@ -304,6 +381,95 @@ __global__ void __launch_bounds__(32 * CT_WARPS, PCX_CT_MINB) ctx_conv_tiled_ker
             const i64 o = ((qn * Co + pout) * oh + th + pad_out) * ow + tw + pad_out;
             if (addsrc != nullptr) sum = __fadd_rn(sum, addsrc[o]);
             out[o] = sum;
+        }
+    }
+}
+
+// Shared-memory form of the tiled kernel (G * GI <= 42 input channels, i.e. valid_dim 56 = model-idx 3).  The kernel above
+// re-reads every input value from L1 / L2 once per (tap, channel group it feeds): 12 % of the FP32 FMA rate, L1 hit rate 19 %,
+// L2-latency-bound (profiles/r1v_ctx_conv_tiled_kernel.json).  Here a block owns CS_ROWS consecutive rows x 128 columns of one
+// band plane, stages their whole 5x5 input window - (CS_ROWS + 4) rows x 132 columns x all input channels, 177 KB - ONCE, and
+// loops over the G channel groups tc itself: each staged value feeds up to 25 taps x 3 outputs x G/2 groups from shared
+// memory.  Eight warps: warp (r, par) takes row r and the channel groups tc = par, par + 2, ...; the two weight sets of an
+// iteration are staged side by side.  Identical chains and fold tree (ct_chain / CtTree): bit-identical outputs.
+constexpr int CS_ROWS = 4;
+constexpr int CS_COLS = 32 * CT_CPT + 4;
+
+template <int GI, int U>
+__global__ void __launch_bounds__(64 * CS_ROWS, 1) ctx_conv_smem_kernel(const float *__restrict__ in, const float *__restrict__ weight,
+                                                                       const float *__restrict__ bias, const float *__restrict__ act,
+                                                                       const float *__restrict__ addsrc, float *__restrict__ out,
+                                                                       int nimg, int npart, int G, int h, int W, int pad_in,
+                                                                       int pad_out, int constrain, Bands bands)
+{
+    extern __shared__ float4 cs_smem[];
+    const int Ci = G * GI, Co = G * 3;
+    const int wslots = Ci * 25;                                            // float4 per weight set
+    float4 *s_w = cs_smem;                                                 // [2][wslots]
+    float *s_in = reinterpret_cast<float *>(cs_smem + 2 * wslots);         // [Ci][CS_ROWS + 4][CS_COLS]
+    const int pn = blockIdx.z, b = pn / nimg, g = blockIdx.y;
+    const int ntile = W / (32 * CT_CPT);
+    const int x0 = (blockIdx.x % ntile) * 32 * CT_CPT, th0 = (blockIdx.x / ntile) * CS_ROWS;
+    const int wl = bands.wl[g];
+    if (x0 >= wl) return;
+    const int ih = h + 2 * pad_in, iw = W + 2 * pad_in;
+    const i64 qn = (i64)pn * npart + g;
+    constexpr int WR = CS_ROWS + 4;
+    // ---- stage the input window: rows th0 - 2 .. th0 + CS_ROWS + 1, columns x0 - 2 .. x0 + 129 of the padded plane
+    {
+        const float *src = in + (qn * Ci * ih + th0 + pad_in - 2) * (i64)iw + x0 + pad_in - 2;
+        const int per_ch = WR * CS_COLS, total = Ci * per_ch;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int c = i / per_ch, r = (i - c * per_ch) / CS_COLS, col = i - c * per_ch - r * CS_COLS;
+            if (th0 + pad_in - 2 + r < ih) cp_async4_ctx(s_in + i, src + ((i64)c * ih + r) * iw + col);
+            else s_in[i] = 0.f;                                            // rows below the plane (h not a multiple of CS_ROWS)
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = warp % CS_ROWS, par = warp / CS_ROWS;
+    const int th = th0 + r;
+    const int c6 = constrain == 6 ? 1 : 0;
+    CtCtx x;
+    x.chs = WR * CS_COLS;
+    x.iw = CS_COLS;
+    x.G = G;
+    x.c6 = c6;
+    x.ws = s_w + par * wslots;
+    x.in_cell = s_in + (r + 2) * CS_COLS + lane + 2;
+    const i64 oh = h + 2 * pad_out, ow = W + 2 * pad_out;
+    for (int t0 = 0; t0 < G; t0 += 2) {
+        __syncthreads();                                                   // the previous pair's weight sets are no longer read
+        // weight rows of the three outputs of (net b, group tc) for tc = t0, t0 + 1: only the reachable channel groups
+        for (int q = 0; q < 2 && t0 + q < G; q++) {
+            const int tcq = t0 + q;
+            int gmax = tcq + 4 + c6;
+            gmax = gmax > G ? G : gmax;
+            const int nw = gmax * GI * 25;
+            float *wd = reinterpret_cast<float *>(s_w + q * wslots);
+            for (int i = threadIdx.x; i < nw * 3; i += blockDim.x) {
+                const int og = i / nw, rr = i % nw;
+                cp_async4_ctx(wd + rr * 4 + og, weight + (((i64)b * Co + tcq * 3 + og) * Ci) * 25 + rr);
+            }
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const int tc = t0 + par;
+        if (tc >= G || th >= h) continue;
+        x.tc = tc;
+        CtAcc acc = U >= 8 ? ct_tree_rt<GI, U - 8 + 1>(x) : CtTree<GI, 0, 1, U>::run(x);      // U = 8 / 9: runtime tree, chain loop x1 / x2
+#pragma unroll
+        for (int c = 0; c < CT_CPT; c++) {
+            const int tw = x0 + lane + 32 * c;
+            if (tw >= wl) continue;
+#pragma unroll
+            for (int og = 0; og < 3; og++) {
+                const int pout = tc * 3 + og, bidx = b * Co + pout;
+                float sum = __fadd_rn(acc.v[c][og], bias[bidx]);
+                if (act != nullptr && sum < 0.f) sum = __fmul_rn(sum, act[bidx]);
+                const i64 o = ((qn * Co + pout) * oh + th + pad_out) * ow + tw + pad_out;
+                if (addsrc != nullptr) sum = __fadd_rn(sum, addsrc[o]);
+                out[o] = sum;
+            }
         }
     }
 }
@@ -1421,6 +1587,42 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
                                                                     n.pad, 0, 1, kind);
                 PCX_LAUNCHED();
             }
+        }
+        static const bool no_smem_form = getenv("PCX_CTX_NO_SMEM") != nullptr;
+        const size_t cs_bytes = (size_t)n.G * l.gi * 25 * 2 * sizeof(float4) + (size_t)n.G * l.gi * (CS_ROWS + 4) * CS_COLS * sizeof(float);
+        // one block per SM (211 KB of shared memory): worth it from two full waves of blocks on (2048x4096: 768 blocks, 40.7 ->
+        // 36.5 ms for the whole entropy encode; a single 512x1024 image is 48 blocks and stays on the L1-resident form)
+        const i64 cs_blocks = (i64)(n.W / (32 * CT_CPT)) * ceil_div(n.h, CS_ROWS) * n.npart * nrep;
+        if (!no_smem_form && l.go == 3 && n.W % (32 * CT_CPT) == 0 && (l.gi == 1 || l.gi == 3) && n.pad == 2 && cs_bytes <= 220 * 1024 &&
+            cs_blocks >= 2 * (i64)pcx_sm_count()) {
+            // shared-memory form: the block stages its 5x5 input window once and loops over the channel groups
+            static int unroll = 0;
+            if (unroll == 0) {
+                const char *e = getenv("PCX_CTX_UNROLL");
+                unroll = e ? atoi(e) : 1;       // measured at 2048x4096 (ms per layer): x1 1.00, x2 1.12, runtime tree 1.25-1.42, full unroll 2.53
+                if (unroll != 2 && unroll != 8 && unroll != 9) unroll = 1;
+                PCX_CUDA(cudaFuncSetAttribute(ctx_conv_smem_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                PCX_CUDA(cudaFuncSetAttribute(ctx_conv_smem_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                PCX_CUDA(cudaFuncSetAttribute(ctx_conv_smem_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                PCX_CUDA(cudaFuncSetAttribute(ctx_conv_smem_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                PCX_CUDA(cudaFuncSetAttribute(ctx_conv_smem_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                PCX_CUDA(cudaFuncSetAttribute(ctx_conv_smem_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                PCX_CUDA(cudaFuncSetAttribute(ctx_conv_smem_kernel<1, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                PCX_CUDA(cudaFuncSetAttribute(ctx_conv_smem_kernel<3, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            }
+            const int ntile = n.W / (32 * CT_CPT);
+            dim3 grid((unsigned)(ntile * ceil_div(n.h, CS_ROWS)), (unsigned)n.npart, (unsigned)nrep);
+#define PCX_CS_LAUNCH(GI_, U_)                                                                                                              \
+    ctx_conv_smem_kernel<GI_, U_><<<grid, 64 * CS_ROWS, cs_bytes, s>>>(l.in, l.weight, l.bias, l.act, l.add, l.out, n.nimg, n.npart, n.G, n.h, \
+                                                                       n.W, n.pad, l.pad_out, l.constrain, bands)
+            if (l.gi == 1) {
+                if (unroll == 1) PCX_CS_LAUNCH(1, 1); else if (unroll == 2) PCX_CS_LAUNCH(1, 2); else if (unroll == 8) PCX_CS_LAUNCH(1, 8); else PCX_CS_LAUNCH(1, 9);
+            } else {
+                if (unroll == 1) PCX_CS_LAUNCH(3, 1); else if (unroll == 2) PCX_CS_LAUNCH(3, 2); else if (unroll == 8) PCX_CS_LAUNCH(3, 8); else PCX_CS_LAUNCH(3, 9);
+            }
+#undef PCX_CS_LAUNCH
+            PCX_LAUNCHED();
+            continue;
         }
         if (l.go == 3 && n.W % (32 * CT_CPT) == 0 && (l.gi == 1 || l.gi == 3)) {
             // tiled throughput form, residual add fused into the store

@@ -329,3 +329,58 @@ def test_other_model_sizes_round_trip(cuda, tmp_path, vd, prex, Hs, Ws):
         lib.pcx_wave_set_fused(1)
     rec = dec.decode_batch(names, Hs, Ws)
     assert tuple(rec.shape) == (2, 3, Hs, Ws) and torch.isfinite(rec).all()
+
+
+def test_graph_replay_equals_eager_and_tracks_parameters(codec):
+    """The channels-last transforms are replayed from a CUDA graph from the third call with the same problem
+    (transforms_nhwc._run_graphed).  Replays must be bit-identical to the eager pass, a new input must flow through the
+    graph's static buffer, and an in-place parameter update or a new shape must drop the capture (never a stale result)."""
+    import torch
+    from pseudocylindrical_convolution_b200 import config
+    enc, dec, x, _ = codec
+    x2 = torch.from_numpy(smooth_images(1, 3, H, W, seed=77)).to(x.device)
+
+    def eager(t):
+        config.CUDA_GRAPHS = False
+        try:
+            return enc.latent(t).clone()
+        finally:
+            config.CUDA_GRAPHS = True
+
+    ref1, ref2 = eager(x), eager(x2)
+    assert not torch.equal(ref1, ref2)
+    enc.encoder.__dict__.pop("_pcx_graph", None)
+    outs = [enc.latent(x).clone() for _ in range(4)]                  # eager, eager + capture, replay, replay
+    st = enc.encoder.__dict__["_pcx_graph"]
+    assert st["graph"] is not None and not st["failed"], "the transform should have been captured"
+    for o in outs:
+        assert torch.equal(o, ref1)
+    assert torch.equal(enc.latent(x2), ref2)                          # replay on a different image
+    # in-place parameter update -> the version stamp changes -> eager pass with the new weights, then a new capture
+    wt = enc.encoder.net[9].weight
+    saved = wt.detach().clone()
+    try:
+        with torch.no_grad():
+            wt.mul_(0.5)
+        ref3 = eager(x)
+        assert not torch.equal(ref3, ref1)
+        for _ in range(3):
+            assert torch.equal(enc.latent(x), ref3)
+    finally:
+        with torch.no_grad():
+            wt.copy_(saved)
+    # a different problem size in between drops the capture; coming back re-captures with identical results
+    xs = torch.from_numpy(smooth_images(1, 3, 256, 512, seed=5)).to(x.device)
+    small = [enc.latent(xs).clone() for _ in range(3)]
+    assert torch.equal(small[0], small[2])
+    for _ in range(3):
+        assert torch.equal(enc.latent(x), ref1)
+    # synthesis side
+    sym = enc.symbols(x)
+    config.CUDA_GRAPHS = False
+    try:
+        rec0 = dec.reconstruct(sym).clone()
+    finally:
+        config.CUDA_GRAPHS = True
+    for _ in range(4):
+        assert torch.equal(dec.reconstruct(sym), rec0)
