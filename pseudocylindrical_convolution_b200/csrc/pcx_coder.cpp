@@ -25,24 +25,34 @@ constexpr uint64_t kQuarter = kHalf >> 1;            // second bit
 constexpr uint64_t kMinRange = (kFull >> 2) + 2;
 constexpr uint64_t kMaxTotal = kMinRange;            // min(2^64/2^32, MIN_RANGE)
 
-// MSB-first bit output: a 64-bit accumulator, whole bytes moved out when it fills (BitIoStream.cpp:52-72 emits the same bytes)
+// The coder's per-symbol work is ~40 arithmetic instructions; what made it 25-45 ns per symbol were its DATA-DEPENDENT
+// branches (how many bits leave, whether underflow bits are pending, the decoder's search): one misprediction costs more
+// than the arithmetic.  Bit I/O below is therefore branch-free: every call moves a 64-bit window to / from memory.
+//
+// MSB-first bit output (BitIoStream.cpp:52-72 emits the same bytes one bit at a time).  `bytes` is kept over-allocated while
+// encoding; `len` counts the bytes that are final and flush() trims the vector to it.
 struct BitSink {
     std::vector<unsigned char> bytes;
+    size_t len = 0;
     uint64_t acc = 0;
-    int nbits = 0;                 // valid low bits of acc, < 8 between calls
-    void put_bits(uint32_t v, int n)            // n <= 32, the n low bits of v, most significant first
+    int nbits = 0;                 // bits of acc not yet final in `bytes`, < 8 between calls
+    void reserve(size_t more)      // room for `more` further bytes (+ the 8-byte store window)
     {
-        if (n <= 0) return;
-        acc = (acc << n) | (uint64_t)(n == 32 ? v : (v & ((1u << n) - 1u)));
-        nbits += n;
-        while (nbits >= 8) {
-            nbits -= 8;
-            bytes.push_back((unsigned char)(acc >> nbits));
-        }
+        if (len + more + 16 > bytes.size()) bytes.resize((len + more + 16) * 2 + 4096);
     }
-    void put(unsigned bit) { put_bits(bit, 1); }
+    inline void put_bits(uint32_t v, int n)     // n in [0, 32]: the n low bits of v, most significant first; caller reserved the room
+    {
+        acc = (acc << n) | ((uint64_t)v & ((1ull << n) - 1ull));
+        nbits += n;                             // <= 39
+        const uint64_t w = __builtin_bswap64((acc << 1) << (63 - nbits));    // pending bits left-aligned (nbits = 0: one junk byte, rewritten later)
+        memcpy(bytes.data() + len, &w, 8);
+        len += (size_t)(nbits >> 3);
+        nbits &= 7;
+    }
+    void put(unsigned bit) { reserve(8); put_bits(bit, 1); }
     void put_run(unsigned bit, uint64_t count)   // `count` copies of one bit
     {
+        reserve((size_t)(count >> 3) + 8);
         const uint32_t pat = bit ? 0xffffffffu : 0u;
         while (count > 0) {
             int n = count > 32 ? 32 : (int)count;
@@ -50,25 +60,38 @@ struct BitSink {
             count -= (uint64_t)n;
         }
     }
-    void flush() { if (nbits != 0) put_bits(0, 8 - nbits); }
+    void flush()                   // zero padding to the byte, then the exact byte count
+    {
+        reserve(8);
+        if (nbits > 0) bytes[len++] = (unsigned char)((acc << (8 - nbits)) & 0xffu);
+        nbits = 0;
+        bytes.resize(len);
+    }
 };
 
-// MSB-first bit input; past the end the stream reads as zeros (ArithmeticCoder.cpp:129-134)
+// MSB-first bit input; past the end the stream reads as zeros (ArithmeticCoder.cpp:129-134): `bytes` carries 16 zero bytes of
+// padding behind the `nbytes` of the stream and the read window is clamped into it.
 struct BitSource {
     std::vector<unsigned char> bytes;
-    size_t pos = 0;
-    uint64_t acc = 0;
-    int left = 0;                  // valid low bits of acc
-    uint32_t get_bits(int n)       // n <= 32
+    size_t nbytes = 0;
+    uint64_t bitpos = 0;
+    void assign(const unsigned char *src, size_t n)
     {
-        if (n <= 0) return 0;
-        while (left < n) {
-            acc = (acc << 8) | (pos < bytes.size() ? bytes[pos] : 0u);
-            pos++;
-            left += 8;
-        }
-        left -= n;
-        return (uint32_t)((acc >> left) & (n == 32 ? 0xffffffffull : ((1ull << n) - 1ull)));
+        bytes.assign(n + 16, 0);
+        if (n) memcpy(bytes.data(), src, n);
+        nbytes = n;
+        bitpos = 0;
+    }
+    inline uint32_t get_bits(int n)       // n in [0, 32]
+    {
+        size_t byte = (size_t)(bitpos >> 3);
+        byte = byte < nbytes + 8 ? byte : nbytes + 8;
+        const int s = (int)(bitpos & 7);
+        uint64_t w;
+        memcpy(&w, bytes.data() + byte, 8);
+        w = __builtin_bswap64(w);
+        bitpos += (uint64_t)n;
+        return (uint32_t)((((w << s) >> 1)) >> (63 - n));
     }
     unsigned get() { return get_bits(1); }
 };
@@ -109,9 +132,16 @@ struct pcx_coder {
         if (n > 0) {
             if (ENC) {
                 const unsigned bit = (unsigned)(low >> (kStateBits - 1));
-                sink.put(bit);
-                if (pending > 0) { sink.put_run(bit ^ 1u, pending); pending = 0; }
-                if (n > 1) sink.put_bits((uint32_t)(low >> (kStateBits - n)), n - 1);
+                if (pending > 0) {
+                    sink.put(bit);
+                    sink.put_run(bit ^ 1u, pending);
+                    pending = 0;
+                    sink.reserve(8);
+                    sink.put_bits((uint32_t)(low >> (kStateBits - n)), n - 1);
+                } else {
+                    sink.reserve(8);
+                    sink.put_bits((uint32_t)(low >> (kStateBits - n)), n);      // the leading bit and the n - 1 that follow it
+                }
             } else {
                 code = n == 32 ? source.get_bits(32) : (((code << n) & kMask) | source.get_bits(n));
             }
@@ -188,19 +218,73 @@ int pcx_coder_start_encoder(pcx_coder *c)
     return PCX_OK;
 }
 
+// Batched forms of narrow<>: the coder state lives in locals for the whole span (the member form reloads it around every byte
+// store), the invariants that cannot fail by construction are checked once on entry, and the decoder finds its symbol by a
+// binary search over the scaled boundaries (cum[j] * range) >> log2(total) instead of the reference's 64-bit division - the
+// symbol is the unique j with boundary(j) <= offset < boundary(j + 1), which is exactly the bracket the division-based form
+// verifies after the fact (ArithmeticCoder.cpp:93-107), so streams, symbols and error cases are unchanged.
 int pcx_coder_encodes(pcx_coder *c, const int32_t *table, int ncode, const int32_t *symbols, int n)
 {
     if (!c || !table || !symbols || ncode < 1 || n < 0) { pcx_set_error("coder: bad encodes arguments"); return PCX_EINVAL; }
     if (!c->encoding) { pcx_set_error("coder: encodes before start_encoder"); return PCX_ECODER; }
+    uint64_t low = c->low, high = c->high, pending = c->pending;
+    if (low >= high || (low & kMask) != low || (high & kMask) != high || high - low + 1 < kMinRange) { pcx_set_error("coder: low/high out of range"); return PCX_ECODER; }
+    BitSink &sink = c->sink;
     const int stride = ncode + 1;
+    int rc = PCX_OK;
     for (int i = 0; i < n; i++) {
         const uint32_t *cum = reinterpret_cast<const uint32_t *>(table + (size_t)i * stride);
-        uint32_t sym = (uint32_t)symbols[i];
-        if (sym >= (uint32_t)ncode) { pcx_set_error("coder: symbol %u outside the %d-entry table", sym, ncode); return PCX_ECODER; }
-        int rc = c->narrow<true>(cum, cum[ncode], sym);
-        if (rc) return rc;
+        const uint32_t sym = (uint32_t)symbols[i];
+        if (sym >= (uint32_t)ncode) { pcx_set_error("coder: symbol %u outside the %d-entry table", sym, ncode); rc = PCX_ECODER; break; }
+        const uint32_t total = cum[ncode], lo = cum[sym], hi = cum[sym + 1];
+        if (lo == hi) { pcx_set_error("coder: symbol %u has zero frequency", sym); rc = PCX_ECODER; break; }
+        if (total > kMaxTotal) { pcx_set_error("coder: total %u too large", total); rc = PCX_ECODER; break; }
+        const uint64_t range = high - low + 1;
+        uint64_t nl, nh;
+        if ((total & (total - 1)) == 0) {                  // every table the GMM stage emits: total = 65536
+            const int sh = __builtin_ctz(total);
+            nl = low + (((uint64_t)lo * range) >> sh);
+            nh = low + (((uint64_t)hi * range) >> sh) - 1;
+        } else {
+            nl = low + (uint64_t)lo * range / total;
+            nh = low + (uint64_t)hi * range / total - 1;
+        }
+        low = nl;
+        high = nh;
+        // Leading bits on which low and high agree leave at once (the reference shifts one per iteration,
+        // ArithmeticCoder.cpp:51-68), then the underflow bits are counted.  range >= 2^30 and total <= 2^30 + 2 keep low < high,
+        // so k <= 31; k = 0 and m = 0 make every expression below an identity - no data-dependent branch except the rare
+        // "pending bits and a long run" case.
+        const int k = __builtin_clz((uint32_t)(low ^ high) | 1u);      // low != high: the | 1 only guards clz(0)
+        const uint32_t head = (uint32_t)((low >> 1) >> (kStateBits - 1 - k));     // the k leading bits of low (k = 0: none)
+        if (__builtin_expect(pending + (uint64_t)k <= 32, 1)) {
+            // first bit b, then `pending` copies of !b, then the other k - 1 bits; nothing at all when k = 0
+            const uint32_t b = (uint32_t)(low >> (kStateBits - 1)) & 1u;
+            const int p = k > 0 ? (int)pending : 0;
+            const uint32_t rest = k > 0 ? head & ((1u << (k - 1)) - 1u) : 0u;
+            const uint64_t fill = b ? 0ull : ((1ull << p) - 1ull);
+            const uint64_t word = k > 0 ? ((((uint64_t)b << p) | fill) << (k - 1)) | rest : 0ull;
+            sink.reserve(8);
+            sink.put_bits((uint32_t)word, k + p);
+            pending -= (uint64_t)p;
+        } else if (k > 0) {
+            const unsigned bit = (unsigned)(low >> (kStateBits - 1));
+            sink.put(bit);
+            sink.put_run(bit ^ 1u, pending);
+            pending = 0;
+            sink.reserve(8);
+            sink.put_bits(head, k - 1);
+        }
+        low = (low << k) & kMask;
+        high = ((high << k) & kMask) | ((1ull << k) - 1ull);
+        const uint32_t under = (uint32_t)(low & ~high) << 1;           // bit 31 <- bit 30: run of positions with low = 1, high = 0
+        const int m = under == 0xffffffffu ? 31 : __builtin_clz(~under);
+        pending += (uint64_t)m;
+        low = (low << m) & (kMask >> 1);                               // bit 31 of low is 0 and of high is 1 here: identities for m = 0
+        high = ((high << m) & (kMask >> 1)) | kHalf | ((1ull << m) - 1ull);
     }
-    return PCX_OK;
+    c->low = low; c->high = high; c->pending = pending;
+    return rc;
 }
 
 int pcx_coder_end_encoder(pcx_coder *c)
@@ -235,9 +319,7 @@ static int begin_decode(pcx_coder *c)
 {
     c->reset();
     c->encoding = false;
-    c->source.pos = 0;
-    c->source.left = 0;
-    c->source.acc = 0;
+    c->source.bitpos = 0;
     c->code = c->source.get_bits(kStateBits);
     return PCX_OK;
 }
@@ -246,7 +328,7 @@ int pcx_coder_start_decoder_mem(pcx_coder *c, const unsigned char *src, long lon
 {
     if (!c || (!src && n > 0) || n < 0) return PCX_EINVAL;
     c->source = BitSource();
-    c->source.bytes.assign(src, src + n);
+    c->source.assign(src, (size_t)n);
     return begin_decode(c);
 }
 
@@ -256,25 +338,67 @@ int pcx_coder_start_decoder(pcx_coder *c)
     FILE *f = fopen(c->path.c_str(), "rb");
     if (!f) { pcx_set_error("coder: cannot open %s for reading", c->path.c_str()); return PCX_EIO; }
     c->source = BitSource();
+    std::vector<unsigned char> all;
     unsigned char buf[1 << 16];
     size_t got;
-    while ((got = fread(buf, 1, sizeof(buf), f)) > 0) c->source.bytes.insert(c->source.bytes.end(), buf, buf + got);
+    while ((got = fread(buf, 1, sizeof(buf), f)) > 0) all.insert(all.end(), buf, buf + got);
     fclose(f);
+    c->source.assign(all.data(), all.size());
     return begin_decode(c);
 }
 
 int pcx_coder_decodes(pcx_coder *c, const int32_t *table, int ncode, int n, float *out_symbols)
 {
     if (!c || !table || !out_symbols || ncode < 1 || n < 0) { pcx_set_error("coder: bad decodes arguments"); return PCX_EINVAL; }
+    uint64_t low = c->low, high = c->high, code = c->code;
+    if (low >= high || (low & kMask) != low || (high & kMask) != high || high - low + 1 < kMinRange) { pcx_set_error("coder: low/high out of range"); return PCX_ECODER; }
+    BitSource &src = c->source;
     const int stride = ncode + 1;
+    int rc = PCX_OK;
     for (int i = 0; i < n; i++) {
         const uint32_t *cum = reinterpret_cast<const uint32_t *>(table + (size_t)i * stride);
-        uint32_t sym = 0;
-        int rc = c->decode_one(cum, (uint32_t)ncode, cum[ncode], &sym);
-        if (rc) return rc;
-        out_symbols[i] = (float)sym;
+        const uint32_t total = cum[ncode];
+        if (total > kMaxTotal || total == 0) { pcx_set_error("coder: total %u too large", total); rc = PCX_ECODER; break; }
+        const uint64_t range = high - low + 1, offset = code - low;
+        const bool p2 = (total & (total - 1)) == 0;
+        const int sh = p2 ? __builtin_ctz(total) : 0;
+        // boundaries of all symbols at once and a branch-free count of those at or below the offset (ncode = 8 in this codec)
+        uint64_t bnd[40];
+        uint32_t a;
+        if (__builtin_expect(ncode <= 32, 1)) {
+            bnd[0] = p2 ? ((uint64_t)cum[0] * range) >> sh : (uint64_t)cum[0] * range / total;
+            uint32_t cnt = 0;
+            for (int j = 1; j <= ncode; j++) {
+                bnd[j] = p2 ? ((uint64_t)cum[j] * range) >> sh : (uint64_t)cum[j] * range / total;
+                cnt += (j < ncode && bnd[j] <= offset) ? 1u : 0u;
+            }
+            a = cnt;                                            // boundaries are non-decreasing: the count is the highest such index
+        } else {
+            pcx_set_error("coder: batched decoding supports at most 32 symbols per table (got %d)", ncode);
+            rc = PCX_EINVAL;
+            break;
+        }
+        const uint64_t ba = bnd[a], bb = bnd[a + 1];
+        if (code < low || offset < ba || bb <= offset) {
+            pcx_set_error("coder: table does not bracket the code value (encoder/decoder CDF mismatch?)");
+            rc = PCX_ECODER;
+            break;
+        }
+        high = low + bb - 1;
+        low = low + ba;
+        const int k = __builtin_clz((uint32_t)(low ^ high) | 1u);      // see pcx_coder_encodes: k <= 31, k = 0 / m = 0 are identities
+        code = ((code << k) & kMask) | src.get_bits(k);
+        low = (low << k) & kMask;
+        high = ((high << k) & kMask) | ((1ull << k) - 1ull);
+        const uint32_t under = (uint32_t)(low & ~high) << 1;
+        const int m = under == 0xffffffffu ? 31 : __builtin_clz(~under);
+        code = (code & kHalf) | ((code << m) & (kMask >> 1)) | src.get_bits(m);
+        low = (low << m) & (kMask >> 1);
+        high = ((high << m) & (kMask >> 1)) | kHalf | ((1ull << m) - 1ull);
+        out_symbols[i] = (float)a;
     }
-    return PCX_OK;
+    c->low = low; c->high = high; c->code = code;
+    return rc;
 }
 
 }  // extern "C"
