@@ -822,12 +822,19 @@ struct StepTap {
     int mode;
 };
 
-// tap at row yi (relative to the band's first row, may be -pad..h+pad-1) and column xi (relative to the first valid column);
-// pa / pb point at channel 0 of the source cell(s) in the channels-last input
-__device__ __forceinline__ StepTap step_resolve(const StepNet &d, const float *in, i64 pn, int cp, int g, int yi, int xi)
+// tap at row yi (relative to the band's first row, may be -pad..h+pad-1) and column xi (relative to the first valid column).
+// The result is independent of the layer: every layer input is a channels-last plane set of the same padded geometry, so a
+// source is identified by its CELL index (offa / offb, to be multiplied by the layer's channels per cell).
+struct StepTapOff {
+    int offa, offb;             // mode 0: value = in[offa]; mode 1: lerp2(in[offa], in[offb], t); mode 2: lerp2(0, in[offb], t); mode 3: 0
+    float t;
+    int mode;
+};
+
+__device__ __forceinline__ StepTapOff step_resolve_off(const StepNet &d, i64 pn, int g, int yi, int xi)
 {
-    StepTap r;
-    r.pa = r.pb = in;
+    StepTapOff r;
+    r.offa = r.offb = 0;
     r.t = 0.f;
     r.mode = 3;
     const int h = d.h, W = d.W, pad = d.pad;
@@ -840,7 +847,7 @@ __device__ __forceinline__ StepTap step_resolve(const StepNet &d, const float *i
         xi -= wlg;
     }
     if (yi >= 0 && yi < h) {
-        r.pa = r.pb = in + (((pn * d.npart + g) * ih + yi + pad) * iw + xi + pad) * cp;
+        r.offa = r.offb = (int)(((pn * d.npart + g) * ih + yi + pad) * iw + xi + pad);
         r.mode = 0;
         return r;
     }
@@ -852,12 +859,22 @@ __device__ __forceinline__ StepTap step_resolve(const StepNet &d, const float *i
     const int q = d.hcol[e];
     const float t = d.htw[e];
     if (q < 0 && t >= d.halo_one) return r;                      // no causal source: the cell stays 0
-    const float *srow = in + (((pn * d.npart + pg) * ih + d.hrow[hr] + pad) * iw + pad) * cp;
+    const i64 srow = ((pn * d.npart + pg) * ih + d.hrow[hr] + pad) * iw + pad;
     const int q1 = (q + 1 == d.bands.wl[pg]) ? 0 : q + 1;
-    r.pa = srow + (i64)(q < 0 ? 0 : q) * cp;
-    r.pb = srow + (i64)q1 * cp;
+    r.offa = (int)(srow + (q < 0 ? 0 : q));
+    r.offb = (int)(srow + q1);
     r.t = t;
     r.mode = q < 0 ? 2 : 1;
+    return r;
+}
+
+__device__ __forceinline__ StepTap step_tap_of(const StepTapOff &o, const float *in, int cp)
+{
+    StepTap r;
+    r.pa = in + (i64)o.offa * cp;
+    r.pb = in + (i64)o.offb * cp;
+    r.t = o.t;
+    r.mode = o.mode;
     return r;
 }
 
@@ -952,9 +969,17 @@ __device__ __forceinline__ void step_stage_weights(const StepNet &d, const StepL
 // lanes m*25 + tap - over the allowed channel groups in ascending order, 8 groups per batch of 128-bit loads.  The chain sums
 // are then moved to the virtual-lane positions (lane t takes lanes t, t+32, t+64 of the reference block) and folded exactly
 // like the reference: [t]+=[t+64], [t]+=[t+32], shuffle-down 16..1.
+// Per-step tap cache (shared memory).  The geometry of a (cell, tap) - which band / row / column it reads, through which halo
+// table entries - does not depend on the layer, but resolving it costs three dependent L2 round trips (plane prefix -> cell
+// record -> halo tables) that used to be paid again in every one of the 12 layers, right on the latency-bound critical path of
+// a step.  The first STEP_CACHE_CELLS cells of a block's work list are resolved ONCE, before the first grid barrier.
+constexpr int STEP_CACHE_CELLS = 64;
+struct StepCellRec { int pn, g, th, tw; };
+
 template <int GI>
 __device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLayer &l, int step, const StepChunk &ch, const int *start,
-                                                const float *ws, int wstride)
+                                                const float *ws, int wstride, const StepTapOff *tap_cache, const StepCellRec *cell_cache,
+                                                int cache_base)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int G = d.G, h = d.h, W = d.W;
@@ -971,16 +996,23 @@ __device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLaye
     gmax = gmax > G ? G : gmax;
     const float4 *wl_ = reinterpret_cast<const float4 *>(ws) + kh * 5 + kw;
     for (int k = warp; k < ch.ncell; k += nwarp) {
-        int img = ch.img0, ce = ch.rem0 + k;                     // (image, cell of the plane) of entry cell0 + k
-        while (ce >= pcells) { ce -= pcells; img++; }
-        const int pn = ch.net * d.nimg + img;
-        const int4 ci = d.cell[first + ce];
-        const int tw = ci.x, g = ci.z, th = ci.w;
+        int pn, tw, g, th;
         StepTap tp;
         tp.pa = tp.pb = l.in;
         tp.t = 0.f;
         tp.mode = 3;
-        if (live) tp = step_resolve(d, l.in, pn, cp, g, th + kh - 2, tw + kw - 2);
+        if (cache_base + k < STEP_CACHE_CELLS) {
+            const StepCellRec cr = cell_cache[cache_base + k];
+            pn = cr.pn; g = cr.g; th = cr.th; tw = cr.tw;
+            if (live) tp = step_tap_of(tap_cache[(cache_base + k) * 25 + lane], l.in, cp);
+        } else {
+            int img = ch.img0, ce = ch.rem0 + k;                 // (image, cell of the plane) of entry cell0 + k
+            while (ce >= pcells) { ce -= pcells; img++; }
+            pn = ch.net * d.nimg + img;
+            const int4 ci = d.cell[first + ce];
+            tw = ci.x; g = ci.z; th = ci.w;
+            if (live) tp = step_tap_of(step_resolve_off(d, pn, g, th + kh - 2, tw + kw - 2), l.in, cp);
+        }
         const int nk = tp.mode == 3 ? 0 : nk_tap;               // a zero input leaves the chains at +0.0f
         // residual source of the three outputs: final since two phases ago, fetched now so that the epilogue waits for nothing
         const i64 o = ((((i64)pn * d.npart + g) * (h + 2 * l.pad_out) + th + l.pad_out) * (W + 2 * l.pad_out) + tw + l.pad_out) * l.cp_out + tc * 3;
@@ -1102,9 +1134,40 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_step_kernel(const __grid_co
     // the block's runs are the same for every layer: decode them ONCE (the walk over the planes costs three integer
     // divisions per plane - done per item by every thread it was half of the kernel's instructions)
     __shared__ StepChunk s_chunk[STEP_MAX_RUNS];
+    __shared__ int s_cache_base[STEP_MAX_RUNS + 1];       // position of a run's first cell in the block's work list
+    __shared__ StepCellRec s_cell[STEP_CACHE_CELLS];
+    __shared__ StepTapOff s_tap[STEP_CACHE_CELLS * 25];
     if (threadIdx.x < nmy && threadIdx.x < STEP_MAX_RUNS)
         s_chunk[threadIdx.x] = step_chunk_of(start, blockIdx.x + threadIdx.x * gridDim.x, p0, np, S, d.nb, d.nimg);
     __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int i = 0; i < nmy && i < STEP_MAX_RUNS; i++) { s_cache_base[i] = acc; acc += s_chunk[i].ncell; }
+        s_cache_base[nmy < STEP_MAX_RUNS ? nmy : STEP_MAX_RUNS] = acc;
+    }
+    __syncthreads();
+    {
+        // resolve the (cell, tap) geometry of the first STEP_CACHE_CELLS cells once for all layers: warp per cell, lane per tap
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+        const int nruns = nmy < STEP_MAX_RUNS ? nmy : STEP_MAX_RUNS;
+        const int ncached = s_cache_base[nruns] < STEP_CACHE_CELLS ? s_cache_base[nruns] : STEP_CACHE_CELLS;
+        for (int f = warp; f < ncached; f += nwarp) {
+            int ci = 0;
+            while (ci + 1 < nruns && s_cache_base[ci + 1] <= f) ci++;
+            const StepChunk ch = s_chunk[ci];
+            const int k = f - s_cache_base[ci];
+            const int pfirst_ = start[ch.plane], pcells = start[ch.plane + 1] - pfirst_;
+            int img = ch.img0, ce = ch.rem0 + k;
+            while (ce >= pcells) { ce -= pcells; img++; }
+            const int pn = ch.net * d.nimg + img;
+            const int4 cinfo = d.cell[pfirst_ + ce];
+            if (lane == 0) s_cell[f] = StepCellRec{pn, cinfo.z, cinfo.w, cinfo.x};
+            if (lane < 25) {
+                const int kw = lane % 5, kh = lane / 5;
+                s_tap[f * 25 + lane] = step_resolve_off(d, pn, cinfo.z, cinfo.w + kh - 2, cinfo.x + kw - 2);
+            }
+        }
+    }                                                     // made visible by the grid barrier (block-level __syncthreads inside)
     if (nitems > 0) {
         const StepChunk c0 = s_chunk[0];
         step_stage_weights(d, d.L[0], c0.net, step - c0.plane, step_ws, wstride);
@@ -1145,8 +1208,9 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_step_kernel(const __grid_co
             cp_async_wait<1>();                        // this item's rows have landed; the next item's may still be in flight
             __syncthreads();
             const float *ws = step_ws + (it & 1) * (4 * wstride + 8);
-            if (d.L[L].gi == 1) step_conv_phase<1>(d, d.L[L], step, ch, start, ws, wstride);
-            else step_conv_phase<3>(d, d.L[L], step, ch, start, ws, wstride);
+            const int cbase = ci < STEP_MAX_RUNS ? s_cache_base[ci] : STEP_CACHE_CELLS;
+            if (d.L[L].gi == 1) step_conv_phase<1>(d, d.L[L], step, ch, start, ws, wstride, s_tap, s_cell, cbase);
+            else step_conv_phase<3>(d, d.L[L], step, ch, start, ws, wstride, s_tap, s_cell, cbase);
         }
         target += gridDim.x;
         grid_barrier(d.bar, target);
