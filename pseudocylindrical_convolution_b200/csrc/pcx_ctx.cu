@@ -330,8 +330,10 @@ __global__ void __launch_bounds__(32 * CT_WARPS, PCX_CT_MINB) ctx_conv_tiled_ker
                                                                        const float *__restrict__ bias, const float *__restrict__ act,
                                                                        const float *__restrict__ addsrc, float *__restrict__ out,
                                                                        int nimg, int npart, int G, int h, int W, int pad_in,
-                                                                       int pad_out, int constrain, Bands bands)
+                                                                       int pad_out, int constrain, Bands bands, int step_lo, int step_hi)
 {
+    // step_lo / step_hi: only the scalars whose wavefront step tw + hp + tc lies in [step_lo, step_hi) are produced (slab-wise
+    // one-shot encoding: the host codes the first slabs' symbols while the device computes the later ones)
     extern __shared__ float4 ct_ws[];
     const int tc = blockIdx.y, pn = blockIdx.z, b = pn / nimg;
     const int Ci = G * GI, Co = G * 3;
@@ -354,6 +356,7 @@ __global__ void __launch_bounds__(32 * CT_WARPS, PCX_CT_MINB) ctx_conv_tiled_ker
     const int hp = rt % Hf, x0 = (rt / Hf) * 32 * CT_CPT;
     const int g = hp / h, th = hp % h, wl = bands.wl[g];
     if (x0 >= wl) return;
+    if (hp + tc + x0 >= step_hi || hp + tc + x0 + 32 * CT_CPT - 1 < step_lo) return;      // no cell of the tile in this slab
     const i64 ih = h + 2 * pad_in, iw = W + 2 * pad_in;
     const i64 qn = (i64)pn * npart + g;
     // W is a multiple of 32*CPT (launcher), so every column of the tile lies inside the padded row; columns >= wl are
@@ -372,7 +375,7 @@ __global__ void __launch_bounds__(32 * CT_WARPS, PCX_CT_MINB) ctx_conv_tiled_ker
 #pragma unroll
     for (int c = 0; c < CT_CPT; c++) {
         const int tw = tw0 + 32 * c;
-        if (tw >= wl) continue;
+        if (tw >= wl || tw + hp + tc < step_lo || tw + hp + tc >= step_hi) continue;
 #pragma unroll
         for (int og = 0; og < 3; og++) {
             const int pout = tc * 3 + og, bidx = b * Co + pout;
@@ -400,7 +403,7 @@ __global__ void __launch_bounds__(64 * CS_ROWS, 1) ctx_conv_smem_kernel(const fl
                                                                        const float *__restrict__ bias, const float *__restrict__ act,
                                                                        const float *__restrict__ addsrc, float *__restrict__ out,
                                                                        int nimg, int npart, int G, int h, int W, int pad_in,
-                                                                       int pad_out, int constrain, Bands bands)
+                                                                       int pad_out, int constrain, Bands bands, int step_lo, int step_hi)
 {
     extern __shared__ float4 cs_smem[];
     const int Ci = G * GI, Co = G * 3;
@@ -412,6 +415,8 @@ __global__ void __launch_bounds__(64 * CS_ROWS, 1) ctx_conv_smem_kernel(const fl
     const int x0 = (blockIdx.x % ntile) * 32 * CT_CPT, th0 = (blockIdx.x / ntile) * CS_ROWS;
     const int wl = bands.wl[g];
     if (x0 >= wl) return;
+    // the block's scalars span the steps [g h + th0 + x0, g h + th0 + CS_ROWS - 1 + x0 + 127 + G - 1]: nothing to do outside the slab
+    if (g * h + th0 + x0 >= step_hi || g * h + th0 + CS_ROWS - 1 + x0 + 32 * CT_CPT - 1 + G - 1 < step_lo) return;
     const int ih = h + 2 * pad_in, iw = W + 2 * pad_in;
     const i64 qn = (i64)pn * npart + g;
     constexpr int WR = CS_ROWS + 4;
@@ -455,12 +460,14 @@ __global__ void __launch_bounds__(64 * CS_ROWS, 1) ctx_conv_smem_kernel(const fl
         __syncthreads();
         const int tc = t0 + par;
         if (tc >= G || th >= h) continue;
+        const int st0 = g * h + th + tc + x0;              // step of the warp's first cell
+        if (st0 >= step_hi || st0 + 32 * CT_CPT - 1 < step_lo) continue;
         x.tc = tc;
         CtAcc acc = U >= 8 ? ct_tree_rt<GI, U - 8 + 1>(x) : CtTree<GI, 0, 1, U>::run(x);      // U = 8 / 9: runtime tree, chain loop x1 / x2
 #pragma unroll
         for (int c = 0; c < CT_CPT; c++) {
             const int tw = x0 + lane + 32 * c;
-            if (tw >= wl) continue;
+            if (tw >= wl || st0 + lane + 32 * c < step_lo || st0 + lane + 32 * c >= step_hi) continue;
 #pragma unroll
             for (int og = 0; og < 3; og++) {
                 const int pout = tc * 3 + og, bidx = b * Co + pout;
@@ -1637,17 +1644,56 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
                                                                 n.input_bias, n.nb, rep_stride);
         PCX_LAUNCHED();
     }
-    const int nitems = n.h_pstart[Hf + n.W + n.pad - 1];
+    // Slabs.  The symbols of wavefront step st depend only on scalars of steps <= st, so the tensor is cut
+    // into consecutive step ranges [slab_lo, slab_hi): slab k runs all layers on its own scalars only, its CDF rows go out and
+    // the host codes them while the device is already computing slab k + 1 - the serial host coder (~12 ns per symbol, as long
+    // as all device work of a 2048x4096 image) is hidden behind the device instead of following it.  Needs the tiled kernels
+    // (they take the step range); any other layer shape falls back to one slab.
+    const int npl_items = Hf + n.W + n.pad - 1;                  // planes of the halo / wrap work lists (h_pstart)
+    bool tiled_all = n.W % (32 * CT_CPT) == 0;
+    for (int L = 0; L < n.nlayers; L++) tiled_all = tiled_all && n.layers[L].go == 3 && (n.layers[L].gi == 1 || n.layers[L].gi == 3);
+    int nslab = 1;
+    {
+        static const char *e = getenv("PCX_WAVE_SLABS");
+        // A tile of the tiled kernels is 128 cells = 128 consecutive steps wide and is recomputed by every slab it touches, so
+        // slabs pay off only when a slab spans several tile widths (measured, entropy encode in ms, 1 / 2 / 4 / 8 slabs:
+        // 512x1024 3.8 / 5.1 / 8.4 / 15.1; 2048x4096 34.0 / 28.8 / 30.4 / 40.2)
+        const int want = e ? atoi(e) : (nsteps >= 1400 ? 3 : (nsteps >= 600 ? 2 : 1));
+        if (tiled_all && want > 1) nslab = want > 16 ? 16 : want;
+        if (nslab > nsteps) nslab = nsteps > 0 ? nsteps : 1;
+    }
+    std::vector<int> slab_end(nslab);                            // first step AFTER slab k, cut at equal shares of the rows
+    for (int k = 0, st = 0; k < nslab; k++) {
+        const long long target = (long long)rowbase[nsteps] * (k + 1) / nslab;
+        while (st < nsteps && (rowbase[st] < target || st <= (k ? slab_end[k - 1] : 0))) st++;
+        slab_end[k] = k == nslab - 1 ? nsteps : st;
+    }
+    static cudaStream_t s_copy = nullptr;                        // CDF rows leave on their own stream, next to the next slab
+    static cudaEvent_t slab_ev[16];
+    if (!s_copy) {
+        PCX_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+        for (auto &e : slab_ev) PCX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    for (int L = 0; L < n.nlayers; L++) {
+        const pcx_wave_layer &l = n.layers[L];
+        const i64 out_elems = (i64)nrep * n.npart * n.G * l.go * (n.h + 2 * l.pad_out) * (n.W + 2 * l.pad_out);
+        PCX_CUDA(cudaMemsetAsync(l.out, 0, sizeof(float) * out_elems, s));
+    }
+    for (int slab = 0; slab < nslab; slab++) {
+    const int slab_lo = nslab == 1 ? 0 : (slab ? slab_end[slab - 1] : 0), slab_hi = nslab == 1 ? 0x7fffffff : slab_end[slab];
+    // halo / wrap cells this slab can read: planes [slab_lo - G - 4, slab_hi) (earlier ones are final, later ones not needed yet)
+    int pl_a = nslab == 1 ? 0 : slab_lo - n.G - 4, pl_b = nslab == 1 ? npl_items : slab_hi;
+    pl_a = pl_a < 0 ? 0 : (pl_a > npl_items ? npl_items : pl_a);
+    pl_b = pl_b > npl_items ? npl_items : pl_b;
+    const int item0 = n.h_pstart[pl_a], nitems = n.h_pstart[pl_b] - n.h_pstart[pl_a];
     for (int L = 0; L < n.nlayers; L++) {
         const pcx_wave_layer &l = n.layers[L];
         const int Ci = n.G * l.gi, Co = n.G * l.go;
-        const i64 out_elems = (i64)nrep * n.npart * Co * (n.h + 2 * l.pad_out) * (n.W + 2 * l.pad_out);
-        PCX_CUDA(cudaMemsetAsync(l.out, 0, sizeof(float) * out_elems, s));
         if (nitems > 0) {
             const i64 total = (i64)nitems * Ci * nrep;
             for (int kind = 0; kind < 2; kind++) {
                 ctx_pad_kernel<<<grid_for(total, 256), 256, 0, s>>>(l.in, bands, n.d_band, n.d_row, n.d_col, n.d_tw,
-                                                                    (const int4 *)n.d_items, 0, nitems, nrep, l.gi, Ci, n.h, n.W,
+                                                                    (const int4 *)n.d_items, item0, nitems, nrep, l.gi, Ci, n.h, n.W,
                                                                     n.pad, 0, 1, kind);
                 PCX_LAUNCHED();
             }
@@ -1678,7 +1724,7 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
             dim3 grid((unsigned)(ntile * ceil_div(n.h, CS_ROWS)), (unsigned)n.npart, (unsigned)nrep);
 #define PCX_CS_LAUNCH(GI_, U_)                                                                                                              \
     ctx_conv_smem_kernel<GI_, U_><<<grid, 64 * CS_ROWS, cs_bytes, s>>>(l.in, l.weight, l.bias, l.act, l.add, l.out, n.nimg, n.npart, n.G, n.h, \
-                                                                       n.W, n.pad, l.pad_out, l.constrain, bands)
+                                                                       n.W, n.pad, l.pad_out, l.constrain, bands, slab_lo, slab_hi)
             if (l.gi == 1) {
                 if (unroll == 1) PCX_CS_LAUNCH(1, 1); else if (unroll == 2) PCX_CS_LAUNCH(1, 2); else if (unroll == 8) PCX_CS_LAUNCH(1, 8); else PCX_CS_LAUNCH(1, 9);
             } else {
@@ -1699,10 +1745,10 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
             }
             if (l.gi == 1)
                 ctx_conv_tiled_kernel<1><<<grid, 32 * CT_WARPS, smem, s>>>(l.in, l.weight, l.bias, l.act, l.add, l.out, n.nimg, n.npart, n.G,
-                                                                          n.h, n.W, n.pad, l.pad_out, l.constrain, bands);
+                                                                          n.h, n.W, n.pad, l.pad_out, l.constrain, bands, slab_lo, slab_hi);
             else
                 ctx_conv_tiled_kernel<3><<<grid, 32 * CT_WARPS, smem, s>>>(l.in, l.weight, l.bias, l.act, l.add, l.out, n.nimg, n.npart, n.G,
-                                                                          n.h, n.W, n.pad, l.pad_out, l.constrain, bands);
+                                                                          n.h, n.W, n.pad, l.pad_out, l.constrain, bands, slab_lo, slab_hi);
             PCX_LAUNCHED();
             continue;
         }
@@ -1724,6 +1770,8 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
             PCX_LAUNCHED();
         }
     }
+    PCX_CUDA(cudaEventRecord(slab_ev[slab], s));
+    }
 
     // ---- CDF rows in coding order, chunk by chunk, host coding pipelined behind the device
     const pcx_wave_layer &last = n.layers[n.nlayers - 1];
@@ -1740,26 +1788,36 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
         total_rows += (long long)per_chunk[b] * n.nimg;
         return pool.run(g_pin.cdf[b], reinterpret_cast<int32_t *>(g_pin.lab[b]), nullptr, per_chunk[b]);
     };
+    int cur_slab = 0;
     while (s0 < nsteps && status == PCX_OK) {
+        while (s0 >= slab_end[cur_slab]) cur_slab++;
+        const int lim = slab_end[cur_slab];                    // a chunk never crosses into a slab that is still being computed
         int s1 = s0 + 1;
-        while (s1 < nsteps && rowbase[s1 + 1] - rowbase[s0] <= cap) s1++;
+        while (s1 < lim && rowbase[s1 + 1] - rowbase[s0] <= cap) s1++;
         const int per = rowbase[s1] - rowbase[s0], b = chunk & 1;
         per_chunk[b] = per;
+        PCX_CUDA(cudaStreamWaitEvent(s_copy, slab_ev[cur_slab], 0));
         if (per > 0) {
             const i64 rows = (i64)per * n.nimg;
-            gmm_ordered_kernel<<<grid_for(rows, 128), 128, 0, s>>>(last.out, d_data, n.d_order, n.d_steptab, n.d_steptab + nsteps + 1,
-                                                                   s0, s1, n.nimg, n.npart, n.G, last.go, n.h, n.W, n.ng, n.nstep,
-                                                                   n.gmm_bias, n.gmm_total, n.gmm_beta, n.d_cdf, n.d_lab);
+            gmm_ordered_kernel<<<grid_for(rows, 128), 128, 0, s_copy>>>(last.out, d_data, n.d_order, n.d_steptab, n.d_steptab + nsteps + 1,
+                                                                        s0, s1, n.nimg, n.npart, n.G, last.go, n.h, n.W, n.ng, n.nstep,
+                                                                        n.gmm_bias, n.gmm_total, n.gmm_beta, n.d_cdf, n.d_lab);
             PCX_LAUNCHED();
-            PCX_CUDA(cudaMemcpyAsync(g_pin.cdf[b], n.d_cdf, sizeof(int32_t) * (size_t)rows * (n.nstep + 1), cudaMemcpyDeviceToHost, s));
-            PCX_CUDA(cudaMemcpyAsync(g_pin.lab[b], n.d_lab, sizeof(int32_t) * (size_t)rows, cudaMemcpyDeviceToHost, s));
+            PCX_CUDA(cudaMemcpyAsync(g_pin.cdf[b], n.d_cdf, sizeof(int32_t) * (size_t)rows * (n.nstep + 1), cudaMemcpyDeviceToHost, s_copy));
+            PCX_CUDA(cudaMemcpyAsync(g_pin.lab[b], n.d_lab, sizeof(int32_t) * (size_t)rows, cudaMemcpyDeviceToHost, s_copy));
         }
-        PCX_CUDA(cudaEventRecord(ev[b], s));
+        PCX_CUDA(cudaEventRecord(ev[b], s_copy));
         if (chunk >= 1) status = code_chunk(b ^ 1);           // code chunk c-1 while chunk c is computed and copied
         s0 = s1;
         chunk++;
     }
     if (status == PCX_OK && chunk >= 1) status = code_chunk((chunk - 1) & 1);
+    // the caller's stream observes the copy stream's work (scratch buffers may be reused right after this call)
+    if (chunk >= 1) {
+        PCX_CUDA(cudaEventRecord(ev[0], s_copy));
+        PCX_CUDA(cudaStreamWaitEvent(s, ev[0], 0));
+        PCX_CUDA(cudaStreamSynchronize(s_copy));
+    }
     for (auto &e : ev) cudaEventDestroy(e);
     if (n_symbols) *n_symbols = total_rows;
     return status;
