@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libpcx.so")
+# PCX_LIB: an alternative build of the same ABI (A/B timing of kernel variants); the default is the in-tree library
+LIB_PATH = os.environ.get("PCX_LIB") or os.path.join(_PKG, "libpcx.so")
 
 PCX_MAX_PART = 32
 

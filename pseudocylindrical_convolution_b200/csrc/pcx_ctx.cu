@@ -463,7 +463,9 @@ __global__ void __launch_bounds__(64 * CS_ROWS, 1) ctx_conv_smem_kernel(const fl
         const int st0 = g * h + th + tc + x0;              // step of the warp's first cell
         if (st0 >= step_hi || st0 + 32 * CT_CPT - 1 < step_lo) continue;
         x.tc = tc;
-        CtAcc acc = U >= 8 ? ct_tree_rt<GI, U - 8 + 1>(x) : CtTree<GI, 0, 1, U>::run(x);      // U = 8 / 9: runtime tree, chain loop x1 / x2
+        CtAcc acc;                                                   // U = 8 / 9: runtime tree, chain loop x1 / x2
+        if constexpr (U >= 8) acc = ct_tree_rt<GI, U - 7>(x);
+        else acc = CtTree<GI, 0, 1, U>::run(x);
 #pragma unroll
         for (int c = 0; c < CT_CPT; c++) {
             const int tw = x0 + lane + 32 * c;
@@ -945,7 +947,10 @@ __device__ __forceinline__ void reg_fence_v4(float4 &a, float4 &b)
 struct StepChunk { int net, plane, cell0, ncell, img0, rem0; };   // cells cell0 .. cell0+ncell of the plane's (image, cell) list;
                                                                   // cell0 = img0 * cells_of_plane + rem0
 
-constexpr int STEP_THREADS = 256;
+#ifndef PCX_STEP_THREADS
+#define PCX_STEP_THREADS 256
+#endif
+constexpr int STEP_THREADS = PCX_STEP_THREADS;
 constexpr int STEP_MAX_RUNS = 32;  // runs of a block whose descriptors are cached in shared memory
 
 __device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc)
