@@ -325,7 +325,7 @@ __device__ __forceinline__ CtAcc ct_tree_rt(const CtCtx &x)
     return acc;
 }
 
-template <int GI>
+template <int GI, int U = 0>
 __global__ void __launch_bounds__(32 * CT_WARPS, PCX_CT_MINB) ctx_conv_tiled_kernel(const float *__restrict__ in, const float *__restrict__ weight,
                                                                        const float *__restrict__ bias, const float *__restrict__ act,
                                                                        const float *__restrict__ addsrc, float *__restrict__ out,
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(32 * CT_WARPS, PCX_CT_MINB) ctx_conv_tiled_ker
     x.c6 = constrain == 6 ? 1 : 0;
     x.ws = ct_ws;
     x.in_cell = in + (qn * Ci * ih + th + pad_in) * iw + tw0 + pad_in;
-    CtAcc r = CtTree<GI, 0, 1>::run(x);
+    CtAcc r = CtTree<GI, 0, 1, U>::run(x);
     const i64 oh = h + 2 * pad_out, ow = W + 2 * pad_out;
 #pragma unroll
     for (int c = 0; c < CT_CPT; c++) {
@@ -403,14 +403,18 @@ __global__ void __launch_bounds__(64 * CS_ROWS, 1) ctx_conv_smem_kernel(const fl
                                                                        const float *__restrict__ bias, const float *__restrict__ act,
                                                                        const float *__restrict__ addsrc, float *__restrict__ out,
                                                                        int nimg, int npart, int G, int h, int W, int pad_in,
-                                                                       int pad_out, int constrain, Bands bands, int step_lo, int step_hi)
+                                                                       int pad_out, int constrain, Bands bands, int step_lo, int step_hi,
+                                                                       int tsplit)
 {
+    // tsplit: the channel-group pairs (tc, tc + 1) of a tile are dealt to `tsplit` blocks (pair index mod tsplit), so that a small
+    // problem still fills the machine; a block stages only the input channels its highest group can reach.
     extern __shared__ float4 cs_smem[];
     const int Ci = G * GI, Co = G * 3;
     const int wslots = Ci * 25;                                            // float4 per weight set
     float4 *s_w = cs_smem;                                                 // [2][wslots]
     float *s_in = reinterpret_cast<float *>(cs_smem + 2 * wslots);         // [Ci][CS_ROWS + 4][CS_COLS]
-    const int pn = blockIdx.z, b = pn / nimg, g = blockIdx.y;
+    const int pn = blockIdx.z / tsplit, tg = blockIdx.z % tsplit, b = pn / nimg, g = blockIdx.y;
+    if (2 * tg >= G) return;
     const int ntile = W / (32 * CT_CPT);
     const int x0 = (blockIdx.x % ntile) * 32 * CT_CPT, th0 = (blockIdx.x / ntile) * CS_ROWS;
     const int wl = bands.wl[g];
@@ -423,7 +427,11 @@ __global__ void __launch_bounds__(64 * CS_ROWS, 1) ctx_conv_smem_kernel(const fl
     // ---- stage the input window: rows th0 - 2 .. th0 + CS_ROWS + 1, columns x0 - 2 .. x0 + 129 of the padded plane
     {
         const float *src = in + (qn * Ci * ih + th0 + pad_in - 2) * (i64)iw + x0 + pad_in - 2;
-        const int per_ch = WR * CS_COLS, total = Ci * per_ch;
+        // highest channel group of this block: the last pair it owns, tc_hi = t0_last + 1; its chains reach groups < tc_hi + 4 (+1)
+        const int npair = (G + 1) / 2, last_pair = tg + ((npair - 1 - tg) / tsplit) * tsplit;
+        int gtop = 2 * last_pair + 1 + 4 + (constrain == 6 ? 1 : 0);
+        gtop = gtop > G ? G : gtop;
+        const int per_ch = WR * CS_COLS, total = gtop * GI * per_ch;
         for (int i = threadIdx.x; i < total; i += blockDim.x) {
             const int c = i / per_ch, r = (i - c * per_ch) / CS_COLS, col = i - c * per_ch - r * CS_COLS;
             if (th0 + pad_in - 2 + r < ih) cp_async4_ctx(s_in + i, src + ((i64)c * ih + r) * iw + col);
@@ -442,7 +450,7 @@ __global__ void __launch_bounds__(64 * CS_ROWS, 1) ctx_conv_smem_kernel(const fl
     x.ws = s_w + par * wslots;
     x.in_cell = s_in + (r + 2) * CS_COLS + lane + 2;
     const i64 oh = h + 2 * pad_out, ow = W + 2 * pad_out;
-    for (int t0 = 0; t0 < G; t0 += 2) {
+    for (int t0 = 2 * tg; t0 < G; t0 += 2 * tsplit) {
         __syncthreads();                                                   // the previous pair's weight sets are no longer read
         // weight rows of the three outputs of (net b, group tc) for tc = t0, t0 + 1: only the reachable channel groups
         for (int q = 0; q < 2 && t0 + q < G; q++) {
@@ -1708,8 +1716,21 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
         // one block per SM (211 KB of shared memory): worth it from two full waves of blocks on (2048x4096: 768 blocks, 40.7 ->
         // 36.5 ms for the whole entropy encode; a single 512x1024 image is 48 blocks and stays on the L1-resident form)
         const i64 cs_blocks = (i64)(n.W / (32 * CT_CPT)) * ceil_div(n.h, CS_ROWS) * n.npart * nrep;
+        // how many blocks share the channel-group pairs of a tile: fewest waves x (staging + pairs per block), measured ~10 us to
+        // stage a window and ~27 us per pair (2048x4096: 1.00 ms per layer with 768 blocks x 7 pairs)
+        int tsplit = 1;
+        {
+            const int npair = (n.G + 1) / 2, sms = pcx_sm_count();
+            double best = 1e30;
+            for (int t = 1; t <= npair; t++) {
+                const double cost = (double)ceil_div(cs_blocks * t, sms) * (10.0 + 27.0 * ceil_div(npair, t));
+                if (cost < best - 1e-9) { best = cost; tsplit = t; }
+            }
+            static const char *e = getenv("PCX_CTX_TSPLIT");
+            if (e && atoi(e) >= 1 && atoi(e) <= npair) tsplit = atoi(e);
+        }
         if (!no_smem_form && l.go == 3 && n.W % (32 * CT_CPT) == 0 && (l.gi == 1 || l.gi == 3) && n.pad == 2 && cs_bytes <= 220 * 1024 &&
-            cs_blocks >= 2 * (i64)pcx_sm_count()) {
+            (i64)nrep * tsplit <= 65535) {
             // shared-memory form: the block stages its 5x5 input window once and loops over the channel groups
             static int unroll = 0;
             if (unroll == 0) {
@@ -1726,10 +1747,10 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
                 PCX_CUDA(cudaFuncSetAttribute(ctx_conv_smem_kernel<3, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             }
             const int ntile = n.W / (32 * CT_CPT);
-            dim3 grid((unsigned)(ntile * ceil_div(n.h, CS_ROWS)), (unsigned)n.npart, (unsigned)nrep);
+            dim3 grid((unsigned)(ntile * ceil_div(n.h, CS_ROWS)), (unsigned)n.npart, (unsigned)(nrep * tsplit));
 #define PCX_CS_LAUNCH(GI_, U_)                                                                                                              \
     ctx_conv_smem_kernel<GI_, U_><<<grid, 64 * CS_ROWS, cs_bytes, s>>>(l.in, l.weight, l.bias, l.act, l.add, l.out, n.nimg, n.npart, n.G, n.h, \
-                                                                       n.W, n.pad, l.pad_out, l.constrain, bands, slab_lo, slab_hi)
+                                                                       n.W, n.pad, l.pad_out, l.constrain, bands, slab_lo, slab_hi, tsplit)
             if (l.gi == 1) {
                 if (unroll == 1) PCX_CS_LAUNCH(1, 1); else if (unroll == 2) PCX_CS_LAUNCH(1, 2); else if (unroll == 8) PCX_CS_LAUNCH(1, 8); else PCX_CS_LAUNCH(1, 9);
             } else {
@@ -1745,15 +1766,23 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
             dim3 grid((unsigned)ceil_div((i64)Hf * ntile, CT_WARPS), (unsigned)n.G, (unsigned)nrep);
             const size_t smem = (size_t)Ci * 25 * sizeof(float4);
             if (smem > 48 * 1024) {                       // 48 channel groups (valid_dim 192): 57.6 KB of weight rows
-                PCX_CUDA(cudaFuncSetAttribute(ctx_conv_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                PCX_CUDA(cudaFuncSetAttribute(ctx_conv_tiled_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                PCX_CUDA(cudaFuncSetAttribute(ctx_conv_tiled_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                PCX_CUDA(cudaFuncSetAttribute(ctx_conv_tiled_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                PCX_CUDA(cudaFuncSetAttribute(ctx_conv_tiled_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                PCX_CUDA(cudaFuncSetAttribute(ctx_conv_tiled_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                PCX_CUDA(cudaFuncSetAttribute(ctx_conv_tiled_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                PCX_CUDA(cudaFuncSetAttribute(ctx_conv_tiled_kernel<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             }
-            if (l.gi == 1)
-                ctx_conv_tiled_kernel<1><<<grid, 32 * CT_WARPS, smem, s>>>(l.in, l.weight, l.bias, l.act, l.add, l.out, n.nimg, n.npart, n.G,
-                                                                          n.h, n.W, n.pad, l.pad_out, l.constrain, bands, slab_lo, slab_hi);
-            else
-                ctx_conv_tiled_kernel<3><<<grid, 32 * CT_WARPS, smem, s>>>(l.in, l.weight, l.bias, l.act, l.add, l.out, n.nimg, n.npart, n.G,
-                                                                          n.h, n.W, n.pad, l.pad_out, l.constrain, bands, slab_lo, slab_hi);
+            static const int ct_unroll = getenv("PCX_CT_UNROLL") ? atoi(getenv("PCX_CT_UNROLL")) : 0;
+#define PCX_CT_LAUNCH(GI_, U_)                                                                                                              \
+    ctx_conv_tiled_kernel<GI_, U_><<<grid, 32 * CT_WARPS, smem, s>>>(l.in, l.weight, l.bias, l.act, l.add, l.out, n.nimg, n.npart, n.G, n.h,  \
+                                                                     n.W, n.pad, l.pad_out, l.constrain, bands, slab_lo, slab_hi)
+            if (l.gi == 1) {
+                if (ct_unroll == 2) PCX_CT_LAUNCH(1, 2); else if (ct_unroll == 4) PCX_CT_LAUNCH(1, 4); else PCX_CT_LAUNCH(1, 0);
+            } else {
+                if (ct_unroll == 2) PCX_CT_LAUNCH(3, 2); else if (ct_unroll == 4) PCX_CT_LAUNCH(3, 4); else PCX_CT_LAUNCH(3, 0);
+            }
+#undef PCX_CT_LAUNCH
             PCX_LAUNCHED();
             continue;
         }
