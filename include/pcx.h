@@ -271,6 +271,11 @@ int pcx_wave_decode(const pcx_wave_net *net, pcx_coder *const *coders, long long
  * mapped pinned memory) when on != 0 (default), or as the launch-per-operator sequence when on == 0.  Same CDFs either way.
  * Returns the previous setting. */
 int pcx_wave_set_fused(int on);
+/* Tuning knobs of the one-shot encoder (pcx_wave_encode_full), for A/B timing and for the tests that pin every variant to the same
+ * bytes: "slabs" = number of wavefront slabs the tensor is encoded in (0 = automatic: 1 below 600 steps, 2 below 1400, else 3),
+ * "tsplit" = blocks sharing the channel-group pairs of a tile in the shared-memory context convolution (0 = cost model),
+ * "smem" = 0 disables that kernel (L1-resident form).  Returns the previous value, or PCX_EINVAL for an unknown name. */
+int pcx_wave_set_option(const char *name, int value);
 
 /* ---- GMM ---------------------------------------------------------------------------------------------
  * EntropyGmmTableOp.forward_batch / forward (main.cpp:49-53 -> entropy_gmm_table_cuda.cu:107-185).

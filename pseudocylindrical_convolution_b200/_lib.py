@@ -86,6 +86,7 @@ PROTOTYPES = {
     "pcx_wave_encode": (_I, [C.POINTER(WaveNet), _P, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), _P]),
     "pcx_wave_encode_full": (_I, [C.POINTER(WaveNet), _P, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), _P]),
     "pcx_wave_set_fused": (_I, [_I]),
+    "pcx_wave_set_option": (_I, [C.c_char_p, _I]),
     "pcx_wave_decode": (_I, [C.POINTER(WaveNet), C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), _P]),
     "pcx_gmm_table": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _I, _P, _P, _P]),
     "pcx_gmm_nll": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),

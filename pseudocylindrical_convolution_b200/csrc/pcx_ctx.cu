@@ -1615,6 +1615,16 @@ int pcx_wave_encode(const pcx_wave_net *net, const float *d_data, pcx_coder *con
 // and fold tree as in the stepwise form, the halo cells are interpolated from the same final values, and the CDF rows are
 // emitted in the stepwise coding order - the bitstream is byte-identical (tests/test_gpu_codec.py).  The rows are produced in
 // chunks of whole steps; the host codes chunk i (one thread per image) while chunk i+1 is computed and copied.
+static std::atomic<int> g_opt_slabs{0}, g_opt_tsplit{0}, g_opt_smem{1};
+
+int pcx_wave_set_option(const char *name, int value)
+{
+    if (!name) return PCX_EINVAL;
+    std::atomic<int> *o = !strcmp(name, "slabs") ? &g_opt_slabs : (!strcmp(name, "tsplit") ? &g_opt_tsplit : (!strcmp(name, "smem") ? &g_opt_smem : nullptr));
+    if (!o) { pcx_set_error("unknown option %s", name); return PCX_EINVAL; }
+    return o->exchange(value);
+}
+
 int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder *const *coders, long long *n_symbols, void *stream)
 {
     int rc = wave_check(net);
@@ -1671,7 +1681,8 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
         // A tile of the tiled kernels is 128 cells = 128 consecutive steps wide and is recomputed by every slab it touches, so
         // slabs pay off only when a slab spans several tile widths (measured, entropy encode in ms, 1 / 2 / 4 / 8 slabs:
         // 512x1024 3.8 / 5.1 / 8.4 / 15.1; 2048x4096 34.0 / 28.8 / 30.4 / 40.2)
-        const int want = e ? atoi(e) : (nsteps >= 1400 ? 3 : (nsteps >= 600 ? 2 : 1));
+        const int opt = g_opt_slabs.load();
+        const int want = opt > 0 ? opt : (e ? atoi(e) : (nsteps >= 1400 ? 3 : (nsteps >= 600 ? 2 : 1)));
         if (tiled_all && want > 1) nslab = want > 16 ? 16 : want;
         if (nslab > nsteps) nslab = nsteps > 0 ? nsteps : 1;
     }
@@ -1728,8 +1739,10 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
             }
             static const char *e = getenv("PCX_CTX_TSPLIT");
             if (e && atoi(e) >= 1 && atoi(e) <= npair) tsplit = atoi(e);
+            const int opt = g_opt_tsplit.load();
+            if (opt >= 1 && opt <= npair) tsplit = opt;
         }
-        if (!no_smem_form && l.go == 3 && n.W % (32 * CT_CPT) == 0 && (l.gi == 1 || l.gi == 3) && n.pad == 2 && cs_bytes <= 220 * 1024 &&
+        if (!no_smem_form && g_opt_smem.load() != 0 && l.go == 3 && n.W % (32 * CT_CPT) == 0 && (l.gi == 1 || l.gi == 3) && n.pad == 2 && cs_bytes <= 220 * 1024 &&
             (i64)nrep * tsplit <= 65535) {
             // shared-memory form: the block stages its 5x5 input window once and loops over the channel groups
             static int unroll = 0;

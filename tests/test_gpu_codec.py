@@ -384,3 +384,33 @@ def test_graph_replay_equals_eager_and_tracks_parameters(codec):
         config.CUDA_GRAPHS = True
     for _ in range(4):
         assert torch.equal(dec.reconstruct(sym), rec0)
+
+
+def test_one_shot_encoder_variants_emit_identical_streams(codec, tmp_path):
+    """The one-shot entropy encoder has three interchangeable execution forms: wavefront slabs (the host codes slab k while the
+    device computes slab k + 1), the shared-memory context convolution with its channel-group pairs dealt to 1..7 blocks, and the
+    L1-resident tiled convolution.  Every combination must write the same bytes as the default, and the default decodes."""
+    import torch
+    from pseudocylindrical_convolution_b200 import _lib
+    enc, dec, x, _ = codec
+    lib = _lib.load()
+    sym = enc.symbols(x)
+
+    def encode(tag, **opts):
+        prev = {k: lib.pcx_wave_set_option(k.encode(), v) for k, v in opts.items()}
+        try:
+            path = str(tmp_path / (tag + ".bin"))
+            enc.ent.encode_batch(sym, [path])
+            return open(path, "rb").read()
+        finally:
+            for k, v in prev.items():
+                lib.pcx_wave_set_option(k.encode(), v)
+
+    ref = encode("default")
+    assert len(ref) > 1000
+    for tag, opts in (("slabs2", dict(slabs=2)), ("slabs3", dict(slabs=3)), ("slabs5_t7", dict(slabs=5, tsplit=7)), ("t1", dict(tsplit=1)),
+                      ("t3", dict(tsplit=3)), ("l1", dict(smem=0)), ("l1_slabs4", dict(smem=0, slabs=4))):
+        assert encode(tag, **opts) == ref, tag
+    assert lib.pcx_wave_set_option(b"nonsense", 1) < 0
+    got = dec.ent.decode_batch(H // 128, W // 8, [str(tmp_path / "default.bin")])
+    assert torch.equal(got, sym)
