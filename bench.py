@@ -56,14 +56,52 @@ def band_widths(Wd):
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples of one GPU while the timed region runs."""
+    """SM clock / throttle-reason samples of one GPU while the timed region runs.  NVML is polled from a thread every 20 ms
+    (the nvidia-smi loop it replaces needs ~0.5 s to start on an 8-GPU box and missed short timed regions altogether);
+    `nvidia-smi -lms` stays as the fallback when the NVML binding is unavailable.  start() may be called before the warm-up:
+    mark() sets the beginning of the timed region and only later samples are reported (all of them if none came later)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.samples, self.stop_flag, self.thread, self.mark_at, self.mx = [], False, None, 0, 0
+
+    def _nvml_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
+
+    def _poll_nvml(self, nv, h):
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = 0.0
+                self.samples.append((float(sm), pw, int(reasons_fn(h))))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)          # fail here, not in the thread
+            self.thread = threading.Thread(target=self._poll_nvml, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -72,11 +110,26 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self):
+        self.mark_at = len(self.samples) if self.proc is None else len(self.lines)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.proc is None and self.thread is not None:                 # NVML
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            use = self.samples[self.mark_at:] or self.samples
+            if not use:
+                return {"sm_mhz": None, "sm_max_mhz": self.mx or None, "reasons": ["no NVML samples"]}
+            sm = sorted(v[0] for v in use)
+            bits = 0
+            for v in use:
+                bits |= v[2]
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.mx or None, "power_w_max": max(v[1] for v in use) or None,
+                    "samples": len(use), "reasons": sorted(n for b, n in self.REASONS if bits & b), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -86,7 +139,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], 0, set(), 0.0
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in (self.lines[self.mark_at:] or self.lines):
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -99,7 +152,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "power_w_max": power or None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def synthetic_image(gen_seed, device):
@@ -281,15 +334,16 @@ def run_gpu(args):
     import pseudocylindrical_convolution_b200.tile_pipeline as tp
     tp.call = call_hook
 
+    sampler = ClockSampler(local)
+    sampler.start()                       # before the warm-up: the sampler is running by the time the timed region starts
     for _ in range(args.warmup):
         pipe(x, out)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = lib.pcx_launch_count()
     timed["on"] = True
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     t0.record()
     for _ in range(args.steps):
         pipe(x, out)
