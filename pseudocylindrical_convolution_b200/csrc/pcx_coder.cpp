@@ -232,6 +232,9 @@ int pcx_coder_encodes(pcx_coder *c, const int32_t *table, int ncode, const int32
     BitSink &sink = c->sink;
     const int stride = ncode + 1;
     int rc = PCX_OK;
+    // room for the whole span up front: a symbol emits at most 31 fresh bits (k <= 31) and the pending run is reserved where it
+    // is flushed, so the common path below never has to check the buffer
+    sink.reserve((size_t)n * 4 + 16);
     for (int i = 0; i < n; i++) {
         const uint32_t *cum = reinterpret_cast<const uint32_t *>(table + (size_t)i * stride);
         const uint32_t sym = (uint32_t)symbols[i];
@@ -264,7 +267,6 @@ int pcx_coder_encodes(pcx_coder *c, const int32_t *table, int ncode, const int32
             const uint32_t rest = k > 0 ? head & ((1u << (k - 1)) - 1u) : 0u;
             const uint64_t fill = b ? 0ull : ((1ull << p) - 1ull);
             const uint64_t word = k > 0 ? ((((uint64_t)b << p) | fill) << (k - 1)) | rest : 0ull;
-            sink.reserve(8);
             sink.put_bits((uint32_t)word, k + p);
             pending -= (uint64_t)p;
         } else if (k > 0) {
@@ -272,7 +274,7 @@ int pcx_coder_encodes(pcx_coder *c, const int32_t *table, int ncode, const int32
             sink.put(bit);
             sink.put_run(bit ^ 1u, pending);
             pending = 0;
-            sink.reserve(8);
+            sink.reserve((size_t)(n - i) * 4 + 16);
             sink.put_bits(head, k - 1);
         }
         low = (low << k) & kMask;
