@@ -269,3 +269,56 @@ def test_coder_errors_are_loud(tmp_path):
     empty = mycoder.coder(str(tmp_path / "none.bin"))
     with pytest.raises(PcxError):
         empty.start_decoder()
+
+
+@pytest.mark.parametrize("ncode", [2, 5, 16, 32])
+def test_coder_other_alphabet_sizes_match_reference(ref_coder, tmp_path, ncode):
+    """The batched decoder counts scaled boundaries instead of dividing (pcx_coder.cpp); the codec only uses 8 symbols, the
+    interface takes any ncode.  Bytes and symbols must match the reference coder for other alphabet sizes, power-of-two and
+    arbitrary totals, ragged spans and a corrupted stream must fail loudly instead of decoding garbage silently."""
+    import torch
+    from pseudocylindrical_convolution_b200 import coder as mycoder
+    from pseudocylindrical_convolution_b200._lib import PcxError
+    if ref_coder is None:
+        pytest.skip("oracle/_ref/coder_ref.so not built")
+    rng = np.random.default_rng(100 + ncode)
+    n = 6000
+    cum = np.zeros((n, ncode + 1), np.int64)
+    for i in range(n):
+        total = 65536 if i % 3 else int(rng.integers(ncode + 1, 1 << 20))
+        w = rng.integers(1, max(2, total // ncode), size=ncode).astype(np.int64)
+        w[int(rng.integers(0, ncode))] += max(0, total - w.sum())
+        cum[i, 1:] = np.cumsum(w)
+    cum = cum.astype(np.int32)
+    sym = rng.integers(0, ncode, size=n).astype(np.int32)
+    t, s_ = torch.from_numpy(cum), torch.from_numpy(sym)
+    mine = mycoder.coder(str(tmp_path / "m.bin"))
+    mine.start_encoder()
+    for a in range(0, n, 1234):
+        b = min(n, a + 1234)
+        mine.encodes(t[a:b].contiguous(), ncode, s_[a:b].contiguous(), b - a)
+    mine.end_encoder()
+    ref = ref_coder.coder(str(tmp_path / "r.bin"))
+    ref.start_encoder(); ref.encodes(t, ncode, s_, n); ref.end_encoder()
+    data = open(tmp_path / "m.bin", "rb").read()
+    assert data == open(tmp_path / "r.bin", "rb").read()
+    d = mycoder.coder(str(tmp_path / "r.bin"))
+    d.start_decoder()
+    out = np.concatenate([d.decodes(t[a:min(n, a + 777)].contiguous(), ncode, min(n, a + 777) - a).numpy() for a in range(0, n, 777)])
+    assert (out.astype(np.int32) == sym).all()
+    r2 = ref_coder.coder(str(tmp_path / "m.bin"))
+    r2.start_decoder()
+    assert (r2.decodes(t, ncode, n).numpy()[:n].astype(np.int32) == sym).all()
+    # a decoder fed different tables than the encoder used either fails loudly or returns different symbols - never crashes
+    other = cum.copy()
+    other[:, 1:-1] = np.sort((other[:, 1:-1].astype(np.int64) * 7 // 8 + 1), axis=1)
+    for j in range(ncode):
+        other[:, j + 1] = np.maximum(other[:, j + 1], other[:, j] + 1)
+    other[:, -1] = np.maximum(other[:, -1], cum[:, -1])
+    d2 = mycoder.coder(str(tmp_path / "m.bin"))
+    d2.start_decoder()
+    try:
+        got = d2.decodes(torch.from_numpy(other.astype(np.int32)), ncode, n).numpy().astype(np.int32)
+        assert got.min() >= 0 and got.max() < ncode
+    except PcxError:
+        pass
