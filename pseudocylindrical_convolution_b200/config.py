@@ -19,4 +19,4 @@ WAVE_ENCODE_FULL = int(os.environ.get("PCX_WAVE_ENCODE_FULL", "1"))
 WAVE_CHUNK_ROWS = int(os.environ.get("PCX_WAVE_CHUNK_ROWS", str(1 << 17)))
 
 # capture the channels-last analysis / synthesis transforms into CUDA graphs (transforms_nhwc._run_graphed)
-CUDA_GRAPHS = True
+CUDA_GRAPHS = os.environ.get("PCX_CUDA_GRAPHS", "1") != "0"
