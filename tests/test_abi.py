@@ -110,3 +110,14 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "libpcx_oracle" in txt or "oracle/_ref" in txt:
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_engine_options_round_trip_without_a_device(lib):
+    """pcx_wave_set_option is plain host state: it returns the previous value and rejects unknown names loudly."""
+    handle = lib.load()
+    for name, default in ((b"slabs", 0), (b"tsplit", 0), (b"smem", 1)):
+        prev = handle.pcx_wave_set_option(name, 5)
+        assert prev == default, (name, prev)
+        assert handle.pcx_wave_set_option(name, prev) == 5
+    assert handle.pcx_wave_set_option(b"no_such_option", 1) < 0
+    assert b"no_such_option" in handle.pcx_last_error()
