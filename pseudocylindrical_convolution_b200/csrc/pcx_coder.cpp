@@ -235,6 +235,12 @@ int pcx_coder_encodes(pcx_coder *c, const int32_t *table, int ncode, const int32
     // room for the whole span up front: a symbol emits at most 31 fresh bits (k <= 31) and the pending run is reserved where it
     // is flushed, so the common path below never has to check the buffer
     sink.reserve((size_t)n * 4 + 16);
+    // the sink's cursor lives in locals too (a byte store through the vector's pointer would otherwise force reloads of its
+    // members); the rare long-run path below goes through the member functions and re-reads them afterwards
+    unsigned char *base = sink.bytes.data();
+    size_t len = sink.len;
+    uint64_t acc = sink.acc;
+    int nbits = sink.nbits;
     for (int i = 0; i < n; i++) {
         const uint32_t *cum = reinterpret_cast<const uint32_t *>(table + (size_t)i * stride);
         const uint32_t sym = (uint32_t)symbols[i];
@@ -267,15 +273,23 @@ int pcx_coder_encodes(pcx_coder *c, const int32_t *table, int ncode, const int32
             const uint32_t rest = k > 0 ? head & ((1u << (k - 1)) - 1u) : 0u;
             const uint64_t fill = b ? 0ull : ((1ull << p) - 1ull);
             const uint64_t word = k > 0 ? ((((uint64_t)b << p) | fill) << (k - 1)) | rest : 0ull;
-            sink.put_bits((uint32_t)word, k + p);
+            const int nb = k + p;                                      // BitSink::put_bits on the local cursor
+            acc = (acc << nb) | (word & ((1ull << nb) - 1ull));
+            nbits += nb;
+            const uint64_t w = __builtin_bswap64((acc << 1) << (63 - nbits));
+            memcpy(base + len, &w, 8);
+            len += (size_t)(nbits >> 3);
+            nbits &= 7;
             pending -= (uint64_t)p;
         } else if (k > 0) {
+            sink.len = len; sink.acc = acc; sink.nbits = nbits;
             const unsigned bit = (unsigned)(low >> (kStateBits - 1));
             sink.put(bit);
             sink.put_run(bit ^ 1u, pending);
             pending = 0;
             sink.reserve((size_t)(n - i) * 4 + 16);
             sink.put_bits(head, k - 1);
+            base = sink.bytes.data(); len = sink.len; acc = sink.acc; nbits = sink.nbits;
         }
         low = (low << k) & kMask;
         high = ((high << k) & kMask) | ((1ull << k) - 1ull);
@@ -285,6 +299,7 @@ int pcx_coder_encodes(pcx_coder *c, const int32_t *table, int ncode, const int32
         low = (low << m) & (kMask >> 1);                               // bit 31 of low is 0 and of high is 1 here: identities for m = 0
         high = ((high << m) & (kMask >> 1)) | kHalf | ((1ull << m) - 1ull);
     }
+    sink.len = len; sink.acc = acc; sink.nbits = nbits;
     c->low = low; c->high = high; c->pending = pending;
     return rc;
 }
