@@ -266,11 +266,16 @@ int pcx_wave_encode(const pcx_wave_net *net, const float *d_data, pcx_coder *con
 int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder *const *coders, long long *n_symbols, void *stream);
 /* Decodes every symbol of the nimg bitstreams; on return layers[0].in holds symbol + input_bias at every valid cell. */
 int pcx_wave_decode(const pcx_wave_net *net, pcx_coder *const *coders, long long *n_symbols, void *stream);
-/* pcx_wave_decode runs each wavefront step as ONE cooperative launch (DInput2, the masked layers with the halo taps interpolated
- * on the fly, residual adds, DExtract2Batch + GMM table, separated by grid barriers; CDF rows and symbols cross PCIe through
- * mapped pinned memory) when on != 0 (default), or as the launch-per-operator sequence when on == 0.  Same CDFs either way.
- * Returns the previous setting. */
-int pcx_wave_set_fused(int on);
+/* Engine behind pcx_wave_decode.  2 (default): ONE persistent dataflow kernel per decode - layers synchronise scalar by scalar
+ * through write-once scratch, images of a batch are independent pipelines, CDF rows (16 bytes) and symbols cross PCIe through
+ * mapped pinned memory, host decoder threads poll them (pcx_flow.cu).  1: one cooperative launch per wavefront step (DInput2,
+ * the masked layers with the halo taps interpolated on the fly, residual adds, DExtract2Batch + GMM table, separated by grid
+ * barriers).  0: the launch-per-operator sequence.  Same CDFs, symbols and error behaviour in all three.  Returns the previous
+ * setting. */
+int pcx_wave_set_fused(int mode);
+/* Host decoder threads of engine 2 per call (0 = automatic: host cores / LOCAL_WORLD_SIZE - 1, at most one per image; the
+ * PCX_CODER_THREADS environment variable overrides the automatic choice).  Returns the previous value. */
+int pcx_flow_set_threads(int n);
 /* Tuning knobs of the one-shot encoder (pcx_wave_encode_full), for A/B timing and for the tests that pin every variant to the same
  * bytes: "slabs" = number of wavefront slabs the tensor is encoded in (0 = automatic: 1 below 600 steps, 2 below 1400, else 3),
  * "tsplit" = blocks sharing the channel-group pairs of a tile in the shared-memory context convolution (0 = cost model),
@@ -315,6 +320,11 @@ int pcx_coder_encodes(pcx_coder *c, const int32_t *table, int ncode, const int32
 int pcx_coder_end_encoder(pcx_coder *c);               /* end_encoder                  */
 int pcx_coder_start_decoder(pcx_coder *c);             /* start_decoder                */
 int pcx_coder_decodes(pcx_coder *c, const int32_t *table, int ncode, int n, float *out_symbols);    /* decodes */
+/* coder.decodes (coder/python.cpp:41-60) for the persistent decoder kernel: `rows` holds one 16-byte record per symbol written by
+ * the device into mapped pinned memory - cum[1..7] as uint16 (cum[0] = 0, cum[8] = 65536 implied) + a 16-bit tag - and rows
+ * [0, n) are decoded for as long as their tag equals tag16 (i.e. as far as the device has got); symbol i goes to out_words[i] as
+ * (word_tag << 8 | symbol), the word the device polls.  *done = rows consumed.  Same arithmetic as pcx_coder_decodes. */
+int pcx_coder_decodes_rows16(pcx_coder *c, const uint16_t *rows, int n, unsigned tag16, unsigned word_tag, uint32_t *out_words, int *done);
 /* in-memory variants for pipelines that keep bitstreams in host RAM */
 int pcx_coder_start_encoder_mem(pcx_coder *c);
 long long pcx_coder_take_bytes(pcx_coder *c, unsigned char *dst, long long cap);

@@ -86,6 +86,7 @@ PROTOTYPES = {
     "pcx_wave_encode": (_I, [C.POINTER(WaveNet), _P, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), _P]),
     "pcx_wave_encode_full": (_I, [C.POINTER(WaveNet), _P, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), _P]),
     "pcx_wave_set_fused": (_I, [_I]),
+    "pcx_flow_set_threads": (_I, [_I]),
     "pcx_wave_set_option": (_I, [C.c_char_p, _I]),
     "pcx_wave_decode": (_I, [C.POINTER(WaveNet), C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), _P]),
     "pcx_gmm_table": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _I, _P, _P, _P]),
@@ -101,6 +102,7 @@ PROTOTYPES = {
     "pcx_coder_end_encoder": (_I, [_P]),
     "pcx_coder_start_decoder": (_I, [_P]),
     "pcx_coder_decodes": (_I, [_P, _P, _I, _I, _P]),
+    "pcx_coder_decodes_rows16": (_I, [_P, _P, _I, C.c_uint, C.c_uint, _P, _IP]),
     "pcx_coder_start_encoder_mem": (_I, [_P]),
     "pcx_coder_take_bytes": (C.c_longlong, [_P, _P, C.c_longlong]),
     "pcx_coder_start_decoder_mem": (_I, [_P, _P, C.c_longlong]),

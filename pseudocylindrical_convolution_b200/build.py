@@ -13,9 +13,10 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(PKG, "libpcx.so")
 
-SOURCES = ["pcx_geometry.cu", "pcx_tile.cu", "pcx_tile_nhwc.cu", "pcx_quant.cu", "pcx_dense.cu", "pcx_conv_tc.cu", "pcx_nhwc_ops.cu", "pcx_ctx.cu", "pcx_metrics.cu",
+SOURCES = ["pcx_geometry.cu", "pcx_tile.cu", "pcx_tile_nhwc.cu", "pcx_quant.cu", "pcx_dense.cu", "pcx_conv_tc.cu", "pcx_nhwc_ops.cu", "pcx_ctx.cu", "pcx_flow.cu", "pcx_metrics.cu",
            "pcx_coder.cpp"]
-HEADERS = [os.path.join(CSRC, "pcx_common.cuh"), os.path.join(PKG, "..", "include", "pcx.h")]
+HEADERS = [os.path.join(CSRC, "pcx_common.cuh"), os.path.join(CSRC, "pcx_ctx_step.cuh"), os.path.join(CSRC, "pcx_flow.h"),
+           os.path.join(PKG, "..", "include", "pcx.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -11,6 +11,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <emmintrin.h>
 #include "../../include/pcx.h"
 
 void pcx_set_error(const char *fmt, ...);
@@ -415,6 +416,59 @@ int pcx_coder_decodes(pcx_coder *c, const int32_t *table, int ncode, int n, floa
         out_symbols[i] = (float)a;
     }
     c->low = low; c->high = high; c->code = code;
+    return rc;
+}
+
+// Decoder side of the persistent wavefront kernel (pcx_flow.cu): the device writes one 16-byte row per symbol into mapped
+// pinned memory - cum[1..7] as uint16 and a 16-bit tag in the last half-word (cum[0] = 0 and cum[8] = 65536 are constants of
+// the GMM stage) - and this function decodes rows [0, n) for as long as their tags equal `tag16`, i.e. as far as the device
+// has got.  Each symbol goes back as one 32-bit word (word_tag << 8 | symbol) that the device polls.  The arithmetic is
+// pcx_coder_decodes with total = 2^16; *done = rows consumed (0 when the first row is not there yet).
+int pcx_coder_decodes_rows16(pcx_coder *c, const uint16_t *rows, int n, unsigned tag16, unsigned word_tag, uint32_t *out_words, int *done)
+{
+    if (!c || !rows || !out_words || !done || n < 0) { pcx_set_error("coder: bad decodes_rows16 arguments"); return PCX_EINVAL; }
+    *done = 0;
+    uint64_t low = c->low, high = c->high, code = c->code;
+    if (low >= high || (low & kMask) != low || (high & kMask) != high || high - low + 1 < kMinRange) { pcx_set_error("coder: low/high out of range"); return PCX_ECODER; }
+    BitSource &src = c->source;
+    int rc = PCX_OK, i = 0;
+    for (; i < n; i++) {
+        // one aligned 16-byte load: the row was written by a single 16-byte store, so the tag vouches for the boundaries
+        __asm__ __volatile__("" ::: "memory");             // re-read memory: the device writes it behind the compiler's back
+        const __m128i v = _mm_load_si128(reinterpret_cast<const __m128i *>(rows + (size_t)i * 8));
+        uint16_t r[8];
+        memcpy(r, &v, 16);
+        if (r[7] != (uint16_t)tag16) break;
+        const uint64_t range = high - low + 1, offset = code - low;
+        uint64_t bnd[9];
+        bnd[0] = 0;
+        uint32_t a = 0;
+        for (int j = 1; j < 8; j++) {
+            bnd[j] = ((uint64_t)r[j - 1] * range) >> 16;
+            a += bnd[j] <= offset ? 1u : 0u;               // boundaries are non-decreasing: the count is the symbol
+        }
+        bnd[8] = range;                                    // (65536 * range) >> 16
+        const uint64_t ba = bnd[a], bb = bnd[a + 1];
+        if (code < low || offset < ba || bb <= offset) {
+            pcx_set_error("coder: table does not bracket the code value (encoder/decoder CDF mismatch?)");
+            rc = PCX_ECODER;
+            break;
+        }
+        high = low + bb - 1;
+        low = low + ba;
+        const int k = __builtin_clz((uint32_t)(low ^ high) | 1u);      // see pcx_coder_encodes: k <= 31, k = 0 / m = 0 are identities
+        code = ((code << k) & kMask) | src.get_bits(k);
+        low = (low << k) & kMask;
+        high = ((high << k) & kMask) | ((1ull << k) - 1ull);
+        const uint32_t under = (uint32_t)(low & ~high) << 1;
+        const int m = under == 0xffffffffu ? 31 : __builtin_clz(~under);
+        code = (code & kHalf) | ((code << m) & (kMask >> 1)) | src.get_bits(m);
+        low = (low << m) & (kMask >> 1);
+        high = ((high << m) & (kMask >> 1)) | kHalf | ((1ull << m) - 1ull);
+        __atomic_store_n(out_words + i, (word_tag << 8) | a, __ATOMIC_RELEASE);
+    }
+    c->low = low; c->high = high; c->code = code;
+    *done = i;
     return rc;
 }
 

@@ -261,9 +261,10 @@ def test_one_shot_encoder_equals_stepwise_engine(codec, tmp_path):
 
 
 def test_fused_step_decoder_equals_operator_sequence(codec, tmp_path):
-    """The decoder's wavefront step as ONE cooperative launch (halo taps interpolated on the fly, grid barriers between the
-    layers, mapped pinned CDF / symbol buffers) must decode the same symbols as the launch-per-operator sequence - for one
-    image and for a batch - from bitstreams written by the one-shot encoder."""
+    """The three decoder engines - 2: one persistent dataflow kernel per decode (pcx_flow.cu: write-once scratch polled scalar by
+    scalar, 16-byte CDF rows and symbol words through mapped pinned memory, per-image pipelines), 1: one cooperative launch per
+    wavefront step with grid barriers, 0: the launch-per-operator sequence - must decode the same symbols, for one image and for
+    a batch, from bitstreams written by the one-shot encoder."""
     import torch
     from pseudocylindrical_convolution_b200 import _lib
     enc, dec, x, _ = codec
@@ -273,7 +274,7 @@ def test_fused_step_decoder_equals_operator_sequence(codec, tmp_path):
     enc.ent.encode_batch(sym.clone(), names)
     lib = _lib.load()
     try:
-        for fused in (1, 0):
+        for fused in (2, 1, 0):
             lib.pcx_wave_set_fused(fused)
             n0 = lib.pcx_launch_count()
             got = dec.ent.decode_batch(H // 128, W // 8, names)
@@ -282,10 +283,44 @@ def test_fused_step_decoder_equals_operator_sequence(codec, tmp_path):
             dec.ent.start(names[1])
             one = dec.ent(H // 128, W // 8)
             assert torch.equal(one, sym[16:32]), "fused=%d: single-image decode differs" % fused
-            if fused:
+            if fused == 1:
                 assert launches <= 204 + 8, launches          # one launch per step (+ the final DInput2 / fill)
+            if fused == 2:
+                assert launches <= 8, launches                # sentinel fill, cell table, THE kernel (+ fill)
+        # engine 2 with fewer host decoder threads than images (one thread serves several pipelines) and repeated calls
+        lib.pcx_wave_set_fused(2)
+        for nthreads in (1, 2):
+            prev = lib.pcx_flow_set_threads(nthreads)
+            try:
+                assert torch.equal(dec.ent.decode_batch(H // 128, W // 8, names), sym), "threads=%d" % nthreads
+            finally:
+                lib.pcx_flow_set_threads(prev)
     finally:
-        lib.pcx_wave_set_fused(1)
+        lib.pcx_wave_set_fused(2)
+
+
+def test_flow_decoder_reports_a_corrupt_stream(codec, tmp_path):
+    """A truncated / foreign bitstream must end the persistent decoder kernel with an error (or, if the garbage happens to stay
+    inside every bracket, with wrong symbols) - never with a hang: the host sets the abort word, every device wait checks it."""
+    import torch
+    from pseudocylindrical_convolution_b200 import _lib
+    enc, dec, x, _ = codec
+    sym = enc.symbols(x)
+    good = str(tmp_path / "g.bin")
+    enc.ent.encode_batch(sym.clone(), [good])
+    data = open(good, "rb").read()
+    bad = str(tmp_path / "b.bin")
+    rng = np.random.default_rng(3)
+    open(bad, "wb").write(bytes(rng.integers(0, 256, size=len(data) // 2, dtype=np.uint8)))
+    lib = _lib.load()
+    lib.pcx_wave_set_fused(2)
+    try:
+        got = dec.ent.decode_batch(H // 128, W // 8, [bad])
+        assert not torch.equal(got, sym)
+    except _lib.PcxError as e:
+        assert "coder" in str(e) or "decoder" in str(e)
+    # the engine is usable afterwards
+    assert torch.equal(dec.ent.decode_batch(H // 128, W // 8, [good]), sym)
 
 
 @pytest.mark.parametrize("vd,prex,Hs,Ws", [(112, "5_112", 512, 1024), (192, "8_192", 256, 512)])
@@ -321,12 +356,12 @@ def test_other_model_sizes_round_trip(cuda, tmp_path, vd, prex, Hs, Ws):
     want = enc.ent.fill(sym.clone())
     lib = _lib.load()
     try:
-        for fused in (1, 0):
+        for fused in (2, 1, 0):
             lib.pcx_wave_set_fused(fused)
             got = dec.ent.decode_batch(Hs // 128, Ws // 8, names)
             assert torch.equal(got, want), "vd %d fused %d" % (vd, fused)
     finally:
-        lib.pcx_wave_set_fused(1)
+        lib.pcx_wave_set_fused(2)
     rec = dec.decode_batch(names, Hs, Ws)
     assert tuple(rec.shape) == (2, 3, Hs, Ws) and torch.isfinite(rec).all()
 

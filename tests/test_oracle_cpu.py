@@ -322,3 +322,66 @@ def test_coder_other_alphabet_sizes_match_reference(ref_coder, tmp_path, ncode):
         assert got.min() >= 0 and got.max() < ncode
     except PcxError:
         pass
+
+
+def test_coder_rows16_decoder_matches_table_decoder(tmp_path):
+    """pcx_coder_decodes_rows16 (the host half of the persistent decoder kernel, pcx_flow.cu): 16-byte rows = cum[1..7] as
+    uint16 + a tag.  Same symbols as the int32-table decoder, stops at the first row whose tag is not the expected one, and
+    writes (word_tag << 8 | symbol) words."""
+    import ctypes as C
+    import torch
+    from pseudocylindrical_convolution_b200 import _lib
+    from pseudocylindrical_convolution_b200 import coder as mycoder
+    rng = np.random.default_rng(11)
+    n = 5000
+    wgt = rng.integers(1, 3000, size=(n, 8)).astype(np.int64)
+    wgt[rng.random(n) < 0.3] = [1, 1, 60000, 1, 1, 1, 1, 1]
+    cum = np.zeros((n, 9), np.int64)
+    cum[:, 1:] = np.cumsum(wgt, 1)
+    cum = cum * 65536 // cum[:, -1:]
+    for j in range(8):
+        cum[:, j + 1] = np.maximum(cum[:, j + 1], cum[:, j] + 1)
+    cum[:, 8] = 65536
+    for j in range(7, 0, -1):
+        cum[:, j] = np.minimum(cum[:, j], cum[:, j + 1] - 1)
+    assert (np.diff(cum, axis=1) > 0).all()
+    sym = rng.integers(0, 8, size=n).astype(np.int32)
+    enc = mycoder.coder(str(tmp_path / "s.bin"))
+    enc.start_encoder()
+    enc.encodes(torch.from_numpy(cum.astype(np.int32)), 8, torch.from_numpy(sym), n)
+    enc.end_encoder()
+    # aligned row buffer: 8 uint16 per row
+    raw = np.zeros(n * 8 + 8, np.uint16)
+    off = (-raw.ctypes.data // 2) % 8
+    rows = raw[off:off + n * 8].reshape(n, 8)
+    assert rows.ctypes.data % 16 == 0
+    rows[:, :7] = cum[:, 1:8].astype(np.uint16)
+    tag = 0x1234
+    avail = 3210
+    rows[:avail, 7] = tag                      # the "device" has produced the first `avail` rows only
+    rows[avail:, 7] = tag - 1
+    words = np.zeros(n, np.uint32)
+    dec = mycoder.coder(str(tmp_path / "s.bin"))
+    dec.start_decoder()
+    done = C.c_int(0)
+    pos = 0
+    _lib.call("pcx_coder_decodes_rows16", dec._h, C.c_void_p(rows.ctypes.data), n, tag, 77, C.c_void_p(words.ctypes.data), C.byref(done))
+    assert done.value == avail
+    pos = done.value
+    _lib.call("pcx_coder_decodes_rows16", dec._h, C.c_void_p(rows[pos:].ctypes.data), n - pos, tag, 77, C.c_void_p(words[pos:].ctypes.data), C.byref(done))
+    assert done.value == 0                     # nothing new
+    rows[avail:, 7] = tag
+    _lib.call("pcx_coder_decodes_rows16", dec._h, C.c_void_p(rows[pos:].ctypes.data), n - pos, tag, 77, C.c_void_p(words[pos:].ctypes.data), C.byref(done))
+    assert done.value == n - avail
+    assert ((words & 0xff).astype(np.int32) == sym).all() and ((words >> 8) == 77).all()
+    # a wrong table is reported like the table decoder reports it
+    bad = mycoder.coder(str(tmp_path / "s.bin"))
+    bad.start_decoder()
+    rows2 = rows.copy()
+    rows2[:, :7] = rows2[::-1, :7]
+    raw2 = np.zeros(n * 8 + 8, np.uint16)
+    off2 = (-raw2.ctypes.data // 2) % 8
+    r2 = raw2[off2:off2 + n * 8].reshape(n, 8)
+    r2[:] = rows2
+    rc = _lib.load().pcx_coder_decodes_rows16(bad._h, C.c_void_p(r2.ctypes.data), n, tag, 77, C.c_void_p(words.ctypes.data), C.byref(done))
+    assert rc in (0, -5) or rc < 0            # garbage tables either mis-decode silently or trip the bracket check; never crash
