@@ -29,6 +29,17 @@
 #define API __attribute__((visibility("default")))
 typedef int64_t i64;
 
+/* The CPU baseline (bench.py --impl reference) runs the wavefront's masked convolution on all host cores: the output scalars of
+ * one step are independent, so the cell loop is an OpenMP parallel-for (each scalar keeps its own reduction order). */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+static int g_orc_threads = 1;
+API void orc_set_threads(int n)
+{
+    g_orc_threads = n < 1 ? 1 : n;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Geometry.  extension/math_cuda.cu:223-253 (sphere_cal_npart_hw_v3); v2 (:177-221) yields the same
  * widths.  weight[] is PCONV_operator/base.py:13-35 set_weight().
@@ -586,21 +597,25 @@ API void orc_ctx_conv_step(const float *in, const float *weight, const float *bi
     int en = psum < Hf + W - 2 ? psum + 1 : Hf + W - 1;
     i64 ih = h + 2 * pad_in, iw = W + 2 * pad_in, oh = h + 2 * pad_out, ow = W + 2 * pad_out;
     i64 Ci = (i64)G * gi, Co = (i64)G * go;
-    for (int pn = 0; pn < nb * nimg; pn++) {
+    const int ncell = start[en] - start[st];
+    const i64 ntask = (i64)nb * nimg * ncell;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(g_orc_threads) if (g_orc_threads > 1 && ntask >= 64)
+#endif
+    for (i64 task = 0; task < ntask; task++) {
+        int pn = (int)(task / ncell), k = start[st] + (int)(task % ncell);
         int b = pn / nimg;
-        for (int k = start[st]; k < start[en]; k++) {
-            int hw = order[k], tw_ = hw % W, hp = hw / W, g = hp / h, th = hp % h;
-            int tc = psum - tw_ - hp;
-            i64 qn = (i64)pn * npart + g;
-            const float *in_cell = in + (qn * Ci * ih + th + pad_in) * iw + tw_ + pad_in;
-            for (int og = 0; og < go; og++) {
-                int pout = tc * go + og;
-                const float *wgt = weight + ((i64)b * Co + pout) * Ci * 25;
-                float s = ctx_conv_scalar(in_cell, wgt, gi, 0, G, ih * iw, iw, hp, tw_, psum, constrain);
-                s = s + bias[(i64)b * Co + pout];
-                if (act && s < 0) s = s * act[(i64)b * Co + pout];
-                out[((qn * Co + pout) * oh + th + pad_out) * ow + tw_ + pad_out] = s;
-            }
+        int hw = order[k], tw_ = hw % W, hp = hw / W, g = hp / h, th = hp % h;
+        int tc = psum - tw_ - hp;
+        i64 qn = (i64)pn * npart + g;
+        const float *in_cell = in + (qn * Ci * ih + th + pad_in) * iw + tw_ + pad_in;
+        for (int og = 0; og < go; og++) {
+            int pout = tc * go + og;
+            const float *wgt = weight + ((i64)b * Co + pout) * Ci * 25;
+            float s = ctx_conv_scalar(in_cell, wgt, gi, 0, G, ih * iw, iw, hp, tw_, psum, constrain);
+            s = s + bias[(i64)b * Co + pout];
+            if (act && s < 0) s = s * act[(i64)b * Co + pout];
+            out[((qn * Co + pout) * oh + th + pad_out) * ow + tw_ + pad_out] = s;
         }
     }
 }

@@ -143,7 +143,8 @@ struct StepTap {
 // The result is independent of the layer: every layer input is a channels-last plane set of the same padded geometry, so a
 // source is identified by its CELL index (offa / offb, to be multiplied by the layer's channels per cell).
 struct StepTapOff {
-    int offa, offb;             // mode 0: value = in[offa]; mode 1: lerp2(in[offa], in[offb], t); mode 2: lerp2(0, in[offb], t); mode 3: 0
+    int offa, offb;             // mode 0: value = in[offa]; mode 1: lerp2(in[offa], in[offb], t); mode 2: lerp2(0, in[offb], t); mode 3: 0;
+                                // mode 4: lerp2(in[offa], 0, 1)
     float t;
     int mode;
 };
@@ -181,7 +182,10 @@ __device__ __forceinline__ StepTapOff step_resolve_off(const StepNet &d, i64 pn,
     r.offa = (int)(srow + (q < 0 ? 0 : q));
     r.offb = (int)(srow + q1);
     r.t = t;
-    r.mode = q < 0 ? 2 : 1;
+    // t == 1 ("left sample only", entropy_context_cuda.cu:146-158: q + 1 > tw): the right neighbour lies on a LATER plane and
+    // does not exist yet when the reference fills this halo cell - it reads the zero-initialised buffer, fma(a, 1, 0 * 0).
+    // Mode 4 reproduces exactly that without touching the neighbour (which the dataflow kernel would otherwise wait for).
+    r.mode = q < 0 ? 2 : (t == 1.0f ? 4 : 1);
     return r;
 }
 
@@ -406,7 +410,7 @@ __device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLaye
             for (int q = 0; q < NQ; q++) xa[q] = xb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
             // both batches of 128-bit loads are in flight before the first FFMA can wait on one
             ld_ca_batch<NQ>(xa, tp.pa + c0 * GI, on && tp.mode != 2);
-            ld_ca_batch<NQ>(xb, tp.pb + c0 * GI, on && tp.mode != 0);
+            ld_ca_batch<NQ>(xb, tp.pb + c0 * GI, on && (tp.mode == 1 || tp.mode == 2));
             float va[8 * GI];
 #pragma unroll
             for (int q = 0; q < NQ; q++) { va[4 * q] = xa[q].x; va[4 * q + 1] = xa[q].y; va[4 * q + 2] = xa[q].z; va[4 * q + 3] = xa[q].w; }
@@ -416,7 +420,7 @@ __device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLaye
                 float vb[8 * GI];
 #pragma unroll
                 for (int q = 0; q < NQ; q++) { vb[4 * q] = xb[q].x; vb[4 * q + 1] = xb[q].y; vb[4 * q + 2] = xb[q].z; vb[4 * q + 3] = xb[q].w; }
-                if (FLOW && on && nk <= c0 + 8) flow_validate<GI>(vb, nk - 1 - c0, tp.pb + (nk - 1) * GI, ctl);
+                if (FLOW && on && nk <= c0 + 8 && tp.mode != 4) flow_validate<GI>(vb, nk - 1 - c0, tp.pb + (nk - 1) * GI, ctl);
 #pragma unroll
                 for (int e = 0; e < 8 * GI; e++) va[e] = lerp2_ref(va[e], vb[e], tp.t);
             }
