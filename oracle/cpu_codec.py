@@ -47,10 +47,6 @@ class CpuCodec:
         self.coder_mod, self.coder_kind = coder_mod, coder_kind
         self.pool = ThreadPoolExecutor(self.threads)
         orc.build()
-        try:
-            orc.lib().orc_set_threads(self.threads)
-        except AttributeError:
-            pass
         self._geom = {}
 
     # ------------------------------------------------------------------------------------------ helpers
@@ -211,7 +207,7 @@ class CpuCodec:
         def layer(k, x, s):
             w, b, a = layers[k]
             orc.ctx_pad_step(x, geom, G, s - 1 if k == 0 else s)
-            orc.ctx_conv_step(x, w, b, a, outs[k], geom, G, 1, 2, 0 if k == 11 else 2, 5 if k == 0 else 6, s)
+            orc.ctx_conv_step(x, w, b, a, outs[k], geom, G, 1, 2, 0 if k == 11 else 2, 5 if k == 0 else 6, s, self.pool, self.threads)
             return outs[k]
 
         for s in range(geom.nsteps(G)):
@@ -301,3 +297,100 @@ def load_reference_coder():
         return mod
     except Exception:
         return None
+
+
+# ---------------------------------------------------------------------------------------------------- checkpoints
+def synth_state_dicts(valid_dim=56, seed=0, channels=192):
+    """Seeded random-init parameters with the reference's key sets, built on the CPU with plain torch modules:
+    (encoder file, decoder file, ent file) dicts = what `{prex}_encoder.pt`, `{prex}_decoder.pt`, `{prex}_ent.pt` hold
+    (pseudo_codec.py:223-227).  Transforms: torch default inits; GDN and quantiser as the reference constructs them
+    (PseudoContextV2.py:159-175, :245-249) with the centres spread over the sigmoid range; entropy net drawn like the training
+    net (kaiming-normal over the causal half of the taps, zero bias, delta-net output bias 2, PReLU slope 0.25 - SURVEY.md H6)."""
+    import math
+    from torch import nn
+    ch, G = channels, valid_dim // 4
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(name, ci, co, k):
+        m = nn.Conv2d(ci, co, k)
+        with torch.no_grad():
+            bound = 1.0 / math.sqrt(ci * k * k)
+            m.weight.copy_((torch.rand(m.weight.shape, generator=g) * 2 - 1) * bound)      # kaiming_uniform(a=sqrt(5)) = U(-1/sqrt(fan_in), .)
+            m.bias.copy_((torch.rand(m.bias.shape, generator=g) * 2 - 1) * bound)
+        sd[name + ".weight"], sd[name + ".bias"] = m.weight.detach().clone(), m.bias.detach().clone()
+
+    def prelu(name, c):
+        sd[name + ".weight"] = torch.full((c,), 0.25)
+
+    def gdn(name, c):
+        ped = torch.tensor([2.0 ** -18]) ** 2
+        sd[name + ".beta"] = torch.sqrt(torch.ones(c) + ped)
+        sd[name + ".gamma"] = torch.sqrt(0.1 * torch.eye(c) + ped)
+
+    def rb(p):
+        conv(p + ".conv1", ch, ch // 2, 1); prelu(p + ".relu1", ch // 2)
+        conv(p + ".conv2", ch // 2, ch // 2, 3); prelu(p + ".relu2", ch // 2)
+        conv(p + ".conv3", ch // 2, ch, 1)
+
+    def att(p):
+        for i in range(3):
+            rb("%s.trunk.%d" % (p, i))
+        for i in range(3):
+            rb("%s.attention.%d" % (p, i))
+        conv(p + ".attention.3", ch, ch, 1)
+
+    def rbv2(p):
+        conv(p + ".conv1", ch, ch, 3); prelu(p + ".relu1", ch)
+        conv(p + ".conv2", ch, ch, 3); prelu(p + ".relu2", ch)
+
+    def down(p, cin):
+        conv(p + ".conv1", cin, ch, 3); prelu(p + ".relu1", ch)
+        conv(p + ".conv2", ch, ch, 3); gdn(p + ".relu2", ch)
+        conv(p + ".short_cut", cin, ch, 1)
+
+    def up(p):
+        conv(p + ".conv1", ch, 4 * ch, 3); prelu(p + ".relu1", 4 * ch)
+        conv(p + ".conv2", ch, ch, 3); gdn(p + ".relu2", ch)
+        conv(p + ".short_cut", ch, 4 * ch, 1)
+
+    e = "encoder.net."
+    down(e + "0", 3); rbv2(e + "1"); down(e + "2", ch); att(e + "3"); rbv2(e + "4"); down(e + "5", ch); rbv2(e + "6")
+    conv(e + "7.conv", ch, ch, 3); att(e + "8"); conv(e + "9", ch, ch, 1)
+    d = "decoder.net."
+    conv(d + "0.conv", ch, ch, 1); att(d + "1"); rbv2(d + "2"); up(d + "3"); rbv2(d + "4"); up(d + "5"); att(d + "6"); rbv2(d + "7")
+    up(d + "8"); rbv2(d + "9"); conv(d + "11", ch, 12, 3)
+    qw = torch.zeros(ch, 8)
+    qw[:, 0] = 0.06
+    qw[:, 1:] = math.log(0.125)
+    sd["quant.weight"] = qw
+    names = ["ent.net.0.conv"] + ["ent.net.%d.%s.conv" % (i, c) for i in range(1, 6) for c in ("conv1", "conv2")] + ["ent.net.6.conv"]
+    for li, n in enumerate(names):
+        cin = G if li == 0 else 3 * G
+        w = torch.randn((3, 3 * G, cin, 5, 5), generator=g) * math.sqrt(2.0 / (cin * 25 / 2.0))
+        b = torch.zeros(3, 3 * G)
+        if li == len(names) - 1:
+            b[1] = 2.0
+        sd[n + ".weight"], sd[n + ".bias"] = w, b
+        if li < len(names) - 1:
+            sd[n + ".relu"] = torch.full((3, 3 * G), 0.25)
+    enc = {k: v for k, v in sd.items() if k.startswith("encoder.")}
+    enc["quant.weight"] = qw.clone()
+    enc["quant.count"] = torch.zeros(ch, 8)
+    dec = {k: v for k, v in sd.items() if k.startswith("decoder.")}
+    dec["quant.weight"] = qw.clone()
+    ent = {k: v for k, v in sd.items() if k.startswith("ent.")}
+    return enc, dec, ent
+
+
+def save_checkpoints(model_dir, prex, valid_dim=56, seed=0):
+    """writes {prex}_encoder.pt / _decoder.pt / _ent.pt (the reference's file convention) and returns (paths, merged dict)"""
+    os.makedirs(model_dir, exist_ok=True)
+    enc, dec, ent = synth_state_dicts(valid_dim, seed)
+    paths = [os.path.join(model_dir, "%s_%s.pt" % (prex, n)) for n in ("encoder", "decoder", "ent")]
+    for p, d in zip(paths, (enc, dec, ent)):
+        torch.save(d, p)
+    merged = dict(enc)
+    merged.update(dec)
+    merged.update(ent)
+    return paths, merged

@@ -286,7 +286,7 @@ def ctx_pad_step(buf, geom, G, psum):
     return buf
 
 
-def ctx_conv_step(x, weight, bias, act, out, geom, G, nimg, pad_in, pad_out, constrain, psum):
+def ctx_conv_step(x, weight, bias, act, out, geom, G, nimg, pad_in, pad_out, constrain, psum, pool=None, threads=1):
     """entropy_conv_cuda_v2.cu:237-290 / :326-379 with the A.6 reduction tree."""
     assert x.dtype == np.float32 and out.dtype == np.float32
     weight, wp = _f(weight)
@@ -297,8 +297,17 @@ def ctx_conv_step(x, weight, bias, act, out, geom, G, nimg, pad_in, pad_out, con
     nb = weight.shape[0]
     go = weight.shape[1] // G
     gi = weight.shape[2] // G
-    lib().orc_ctx_conv_step(_fp(x), wp, bp, ap, _fp(out), nb, int(nimg), geom.npart, int(G), gi, go, geom.h, geom.W,
-                            int(pad_in), int(pad_out), int(constrain), int(psum), _ip(geom.order), _ip(geom.start))
+    args = (_fp(x), wp, bp, ap, _fp(out), nb, int(nimg), geom.npart, int(G), gi, go, geom.h, geom.W,
+            int(pad_in), int(pad_out), int(constrain), int(psum), _ip(geom.order), _ip(geom.start))
+    lo, hi = geom.window(psum, G)
+    ntask = nb * int(nimg) * (hi - lo)
+    if pool is not None and threads > 1 and ntask >= 4 * threads and psum < geom.nsteps(G):
+        # CPU baseline: the step's independent scalars spread over the host cores (ctypes releases the GIL)
+        step = -(-ntask // threads)
+        list(pool.map(lambda a: lib().orc_ctx_conv_step_range(*args, C.c_int64(a), C.c_int64(min(a + step, ntask))),
+                      range(0, ntask, step)))
+    else:
+        lib().orc_ctx_conv_step(*args)
     return out
 
 

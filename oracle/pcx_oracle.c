@@ -29,16 +29,6 @@
 #define API __attribute__((visibility("default")))
 typedef int64_t i64;
 
-/* The CPU baseline (bench.py --impl reference) runs the wavefront's masked convolution on all host cores: the output scalars of
- * one step are independent, so the cell loop is an OpenMP parallel-for (each scalar keeps its own reduction order). */
-#ifdef _OPENMP
-#include <omp.h>
-#endif
-static int g_orc_threads = 1;
-API void orc_set_threads(int n)
-{
-    g_orc_threads = n < 1 ? 1 : n;
-}
 
 /* ------------------------------------------------------------------------------------------------
  * Geometry.  extension/math_cuda.cu:223-253 (sphere_cal_npart_hw_v3); v2 (:177-221) yields the same
@@ -586,9 +576,13 @@ static float ctx_conv_scalar(const float *in_cell, const float *wgt, int gi, int
 
 /* in  (nb*nimg*npart, G*gi, h+2pi, W+2pi), weight (nb, G*go, G*gi, 5, 5), bias/act (nb, G*go),
  * out (nb*nimg*npart, G*go, h+2po, W+2po).  act == NULL -> no PReLU. */
-API void orc_ctx_conv_step(const float *in, const float *weight, const float *bias, const float *act,
-                           float *out, int nb, int nimg, int npart, int G, int gi, int go, int h, int W,
-                           int pad_in, int pad_out, int constrain, int psum, const int *order, const int *start)
+/* The output scalars of one step are independent: tasks [task_lo, task_hi) of the nb*nimg*cells (net image, cell) pairs, so
+ * that the CPU baseline (bench.py --impl reference) can spread a step over the host cores (oracle.py splits the range over a
+ * thread pool; every scalar keeps its own reduction order).  task_hi < 0 = all. */
+API void orc_ctx_conv_step_range(const float *in, const float *weight, const float *bias, const float *act,
+                                 float *out, int nb, int nimg, int npart, int G, int gi, int go, int h, int W,
+                                 int pad_in, int pad_out, int constrain, int psum, const int *order, const int *start,
+                                 i64 task_lo, i64 task_hi)
 {
     int Hf = h * npart;
     int mod = Hf + W + G - 2;
@@ -599,10 +593,8 @@ API void orc_ctx_conv_step(const float *in, const float *weight, const float *bi
     i64 Ci = (i64)G * gi, Co = (i64)G * go;
     const int ncell = start[en] - start[st];
     const i64 ntask = (i64)nb * nimg * ncell;
-#ifdef _OPENMP
-#pragma omp parallel for schedule(static) num_threads(g_orc_threads) if (g_orc_threads > 1 && ntask >= 64)
-#endif
-    for (i64 task = 0; task < ntask; task++) {
+    if (task_hi < 0 || task_hi > ntask) task_hi = ntask;
+    for (i64 task = task_lo < 0 ? 0 : task_lo; task < task_hi; task++) {
         int pn = (int)(task / ncell), k = start[st] + (int)(task % ncell);
         int b = pn / nimg;
         int hw = order[k], tw_ = hw % W, hp = hw / W, g = hp / h, th = hp % h;
@@ -618,6 +610,14 @@ API void orc_ctx_conv_step(const float *in, const float *weight, const float *bi
             out[((qn * Co + pout) * oh + th + pad_out) * ow + tw_ + pad_out] = s;
         }
     }
+}
+
+API void orc_ctx_conv_step(const float *in, const float *weight, const float *bias, const float *act,
+                           float *out, int nb, int nimg, int npart, int G, int gi, int go, int h, int W,
+                           int pad_in, int pad_out, int constrain, int psum, const int *order, const int *start)
+{
+    orc_ctx_conv_step_range(in, weight, bias, act, out, nb, nimg, npart, G, gi, go, h, W, pad_in, pad_out, constrain, psum, order,
+                            start, 0, -1);
 }
 
 /* entropy_add_cuda.cu:25-44: y += x at the wavefront cells (both (nrep*npart, G*cpg, h+2p, W+2p)). */

@@ -434,8 +434,11 @@ int pcx_coder_decodes_rows16(pcx_coder *c, const uint16_t *rows, int n, unsigned
     int rc = PCX_OK, i = 0;
     for (; i < n; i++) {
         // one aligned 16-byte load: the row was written by a single 16-byte store, so the tag vouches for the boundaries
-        __asm__ __volatile__("" ::: "memory");             // re-read memory: the device writes it behind the compiler's back
-        const __m128i v = _mm_load_si128(reinterpret_cast<const __m128i *>(rows + (size_t)i * 8));
+        // ONE 16-byte load, forced (a plain _mm_load_si128 is an ordinary dereference: the optimiser narrowed it into separate
+        // loads and read the boundaries BEFORE the tag - a row landing in between was accepted with the previous step's
+        // boundaries).  The device wrote the row with a single 16-byte store, so tag and boundaries are one snapshot.
+        __m128i v;
+        __asm__ __volatile__("movdqa %1, %0" : "=x"(v) : "m"(*reinterpret_cast<const __m128i *>(rows + (size_t)i * 8)) : "memory");
         uint16_t r[8];
         memcpy(r, &v, 16);
         if (r[7] != (uint16_t)tag16) break;

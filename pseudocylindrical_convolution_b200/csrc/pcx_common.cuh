@@ -11,6 +11,7 @@ typedef long long i64;
 
 // ---------------------------------------------------------------------------------------------- errors
 void pcx_set_error(const char *fmt, ...);
+void pcx_append_error(const char *fmt, ...);     // adds context to the message of the error being returned
 extern std::atomic<long long> g_pcx_launches;
 
 #define PCX_REQUIRE(cond, ...)                                   \

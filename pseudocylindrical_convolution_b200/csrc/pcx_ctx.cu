@@ -1557,6 +1557,7 @@ static int wave_decode_fused(const pcx_wave_net &n, pcx_coder *const *coders, lo
     pool.start(coders, n.nimg, n.nstep, false);
     long long total = 0;
     unsigned bar_base = 0;
+    FILE *dump = getenv("PCX_WAVE_DUMP") ? fopen(getenv("PCX_WAVE_DUMP"), "w") : nullptr;
     int pfirst = 0, pcount = 0;
     for (int step = 0; step < nsteps; step++) {
         int p0 = step - n.G + 1 < 0 ? 0 : step - n.G + 1;
@@ -1592,7 +1593,16 @@ static int wave_decode_fused(const pcx_wave_net &n, pcx_coder *const *coders, lo
         auto t2 = std::chrono::steady_clock::now();
         if (count > 0) {
             rc = pool.run(g_pin.cdf[0], nullptr, g_pin.lab[0], count);
-            if (rc < 0) return rc;
+            if (dump) {                                 // PCX_WAVE_DUMP=<file>: same text as the dataflow engine writes (debugging)
+                for (int im = 0; im < n.nimg; im++)
+                    for (int r = 0; r < count; r++) {
+                        const int32_t *row = g_pin.cdf[0] + ((size_t)im * count + r) * 9;
+                        fprintf(dump, "%d %d %d |", im, step, r);
+                        for (int j = 1; j < 8; j++) fprintf(dump, " %d", row[j]);
+                        fprintf(dump, " | %d\n", (int)g_pin.lab[0][(size_t)im * count + r]);
+                    }
+            }
+            if (rc < 0) { if (dump) fclose(dump); return rc; }
             total += (long long)count * n.nimg;
         }
         if (h_dbg) {
@@ -1605,6 +1615,7 @@ static int wave_decode_fused(const pcx_wave_net &n, pcx_coder *const *coders, lo
         pcount = count;
     }
     cudaFree(d_start);
+    if (dump) fclose(dump);
     // the last step's symbols never pass through the network: one more DInput2 (pseudo_codec.py:159)
     rc = pcx_dinput_step(dev_prev, n.layers[0].in, n.nimg, n.npart, n.G, n.h, n.W, n.pad, n.input_bias, n.nb, nsteps, n.d_order, n.h_start, s);
     if (rc < 0) return rc;

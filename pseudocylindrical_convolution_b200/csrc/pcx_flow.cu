@@ -352,7 +352,9 @@ int pcx_wave_decode_flow(const pcx_wave_net &n, pcx_coder *const *coders, long l
     if (smem > (size_t)(st.max_smem - 48 * 1024)) { *unsupported = true; return PCX_OK; }
     PCX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wave_flow_kernel, threads, smem));
     const int max_grid = pcx_sm_count() * per_sm;
-    const int B = n.nimg > 0 ? max_grid / n.nimg : 0;            // blocks per image
+    int B = n.nimg > 0 ? max_grid / n.nimg : 0;                  // blocks per image
+    if (const char *e = getenv("PCX_FLOW_BLOCKS")) B = atoi(e) >= 2 && atoi(e) < B ? atoi(e) : B;      // debugging / tuning
+    const int smax = getenv("PCX_FLOW_SMAX") ? atoi(getenv("PCX_FLOW_SMAX")) : 0;
     if (per_sm < 1 || B < 2 || nsteps >= 65534) { *unsupported = true; return PCX_OK; }
 
     // ---- per-step schedule (per image): runs of at most S cells per (net, plane); block i of the image takes runs i, i + B, ...
@@ -370,7 +372,7 @@ int pcx_wave_decode_flow(const pcx_wave_net &n, pcx_coder *const *coders, long l
         for (int q = p0; q < p1; q++) maxcells = std::max(maxcells, n.h_start[q + 1] - n.h_start[q]);
         int S = wpb, nchunk = 0;
         long best = -1;
-        for (int cand = wpb; cand < maxcells + wpb; cand += wpb) {
+        for (int cand = wpb; cand < maxcells + wpb && (smax <= 0 || cand <= smax || cand == wpb); cand += wpb) {
             int chunks = 0;
             for (int q = p0; q < p1; q++) chunks += n.nb * ceil_div(n.h_start[q + 1] - n.h_start[q], cand);
             const long cost = (long)ceil_div(chunks, B) * (cand / wpb);
@@ -506,14 +508,21 @@ int pcx_wave_decode_flow(const pcx_wave_net &n, pcx_coder *const *coders, long l
     g_pcx_launches.fetch_add(1, std::memory_order_relaxed);
 
     // ---- host decoders: T threads, thread t serves images t, t + T, ...; each image is its own state machine
-    const int T = flow_host_threads(n.nimg);
+    const int T = getenv("PCX_WAVE_DUMP") ? 1 : flow_host_threads(n.nimg);
     std::atomic<int> status{PCX_OK};
     std::atomic<long long> total{0};
+    std::mutex msg_mu;
+    std::string message;
+    std::vector<uint4> log_rows;
+    std::vector<int4> log_meta;
+    FILE *dump = nullptr;                              // PCX_WAVE_DUMP=<file>: every decoded row (debugging; one host thread)
+    if (const char *e = getenv("PCX_WAVE_DUMP")) dump = fopen(e, "w");
     volatile unsigned *h_ctl = st.h_ctl;
     auto serve = [&](int t0) {
         struct Img { int step, pos; bool done; };
         std::vector<Img> im;
         std::vector<int> ids;
+        std::vector<uint4> snap;
         for (int i = t0; i < n.nimg; i += T) { ids.push_back(i); im.push_back({0, 0, false}); }
         size_t left = ids.size();
         long long mine = 0;
@@ -529,9 +538,28 @@ int pcx_wave_decode_flow(const pcx_wave_net &n, pcx_coder *const *coders, long l
                 const int cnt = counts[m.step], i = ids[q];
                 const size_t base = (size_t)i * rows_cap + m.pos;
                 int got = 0;
-                const int rc = pcx_coder_decodes_rows16(coders[i], reinterpret_cast<const uint16_t *>(st.h_rows + base), cnt - m.pos,
-                                                        (unsigned)(m.step + 1) & 0xffffu, (unsigned)(m.step + 1), st.h_symw + base, &got);
-                if (rc < 0) { status.store(rc); break; }
+                const uint16_t *src = reinterpret_cast<const uint16_t *>(st.h_rows + base);
+                if (dump) {                            // decode from a snapshot: the device reuses a row as soon as the step is decoded
+                    snap.resize((size_t)(cnt - m.pos));
+                    memcpy(snap.data(), st.h_rows + base, sizeof(uint4) * (size_t)(cnt - m.pos));
+                    src = reinterpret_cast<const uint16_t *>(snap.data());
+                }
+                const int rc = pcx_coder_decodes_rows16(coders[i], src, cnt - m.pos, (unsigned)(m.step + 1) & 0xffffu,
+                                                        (unsigned)(m.step + 1), st.h_symw + base, &got);
+                if (dump && got > 0) {                  // kept in memory, written after the decode: the host must stay fast
+                    for (int r = 0; r < got; r++) {
+                        uint4 rec = snap[(size_t)r];
+                        log_rows.push_back(rec);
+                        log_meta.push_back(make_int4(i, m.step, m.pos + r, (int)(st.h_symw[base + r] & 0xffu)));
+                    }
+                }
+                if (rc < 0) {
+                    // the message lives in this thread's error slot: hand it to the calling thread
+                    pcx_append_error(" [image %d, wavefront step %d, row %d of %d]", i, m.step, m.pos + got, cnt);
+                    std::lock_guard<std::mutex> lk(msg_mu);
+                    if (status.load() == PCX_OK) { message = pcx_last_error(); status.store(rc); }
+                    break;
+                }
                 if (got > 0) {
                     progressed = true;
                     m.pos += got;
@@ -557,6 +585,15 @@ int pcx_wave_decode_flow(const pcx_wave_net &n, pcx_coder *const *coders, long l
     for (int t = 1; t < T; t++) workers.emplace_back(serve, t);
     serve(0);
     for (auto &w : workers) w.join();
+    if (dump) {
+        for (size_t q = 0; q < log_rows.size(); q++) {
+            const uint16_t *row = reinterpret_cast<const uint16_t *>(&log_rows[q]);
+            fprintf(dump, "%d %d %d |", log_meta[q].x, log_meta[q].y, log_meta[q].z);
+            for (int j = 0; j < 7; j++) fprintf(dump, " %u", (unsigned)row[j]);
+            fprintf(dump, " | %d\n", log_meta[q].w);
+        }
+        fclose(dump);
+    }
     const int rc = status.load();
     if (rc != PCX_OK) h_ctl[0] = 1;                       // tell the kernel to stop waiting
     cudaError_t se = cudaStreamSynchronize(s);
@@ -578,7 +615,10 @@ int pcx_wave_decode_flow(const pcx_wave_net &n, pcx_coder *const *coders, long l
         pcx_set_error("decoder kernel gave up waiting (code %u): host decoder stalled or device time-out", dev_err);
         return PCX_ECUDA;
     }
-    if (rc != PCX_OK) return rc;                           // the coder's message is already set
+    if (rc != PCX_OK) {
+        if (!message.empty()) pcx_set_error("%s", message.c_str());
+        return rc;
+    }
     if (n_symbols) *n_symbols = total.load();
     return PCX_OK;
 }

@@ -21,6 +21,16 @@ void pcx_set_error(const char *fmt, ...)
     va_end(ap);
 }
 
+void pcx_append_error(const char *fmt, ...)
+{
+    const size_t n = strlen(g_err);
+    if (n + 1 >= sizeof(g_err)) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err + n, sizeof(g_err) - n, fmt, ap);
+    va_end(ap);
+}
+
 int pcx_sm_count()
 {
     static int cached = 0;
