@@ -237,6 +237,19 @@ class PseudoEncoder(nn.Module):
             self.ent.encode_batch(self.symbols(x), code_names)
 
 
+def _encode_images(self, images_u8, code_names):
+    """Host-facing batch entry point: images_u8 is a uint8 (N, H, W, 3) tensor in (ideally pinned) HOST memory, as cv2.imread
+    delivers it; the copy to the device, the /255 conversion (img2tensor, reference :215-217), the transforms, the wavefront and
+    the host range coder all run inside this call; one bitstream file per image."""
+    dev = next(self.encoder.parameters()).device
+    with torch.no_grad():
+        x = images_u8.to(dev, non_blocking=True).permute(0, 3, 1, 2).to(torch.float32).div_(255.).contiguous()
+        self.encode_batch(x, code_names)
+
+
+PseudoEncoder.encode_images = _encode_images
+
+
 class PseudoDecoder(nn.Module):
 
     def __init__(self, valid_dim, device_id):
@@ -283,6 +296,23 @@ def _decode_batch(self, code_names, height=512, width=1024):
 
 
 PseudoDecoder.decode_batch = _decode_batch
+
+
+def _decode_images(self, code_names, out_u8=None, height=512, width=1024):
+    """Inverse of PseudoEncoder.encode_images: N bitstream files -> uint8 (N, H, W, 3) images in host memory (written into
+    out_u8 when given, e.g. a pinned buffer).  tensor2img (reference :219-221) with the value range made explicit: the leaky
+    ClipData output is clamped to [0, 255] before the truncating conversion."""
+    with torch.no_grad():
+        rec = self.decode_batch(code_names, height, width)
+        img = rec.mul(255.).clamp_(0., 255.).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+        if out_u8 is None:
+            return img.cpu()
+        out_u8.copy_(img, non_blocking=True)
+        torch.cuda.current_stream(img.device).synchronize()
+        return out_u8
+
+
+PseudoDecoder.decode_images = _decode_images
 
 
 def img2tensor(img, device):
