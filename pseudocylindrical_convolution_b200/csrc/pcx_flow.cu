@@ -35,7 +35,8 @@ namespace {
 
 struct FlowNet {
     StepNet net;                  // net.prev / net.cdf / net.bar are unused here
-    int nsteps, rows_cap, blocks_per_img, pad0;
+    int nsteps, rows_cap, blocks_per_img;
+    unsigned tag_salt;            // per-call salt of the row / symbol tags: a word left over from an earlier decode never matches
     const int *start;             // device copy of the plane prefix of the wavefront order (Hf + W entries)
     const int4 *sched;            // per step: first plane, planes, run length, runs (per image)
     uint4 *rows;                  // mapped host memory: (nimg, rows_cap) CDF rows, 7 x uint16 boundaries + uint16 tag (step + 1)
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_flow_kernel(const __grid_co
         }
         const int nmy = bi < nchunk ? (nchunk - 1 - bi) / B + 1 : 0;      // my runs per layer
         const int nitems = nmy * d.nlayers;
-        if (tracer) f.trace[(size_t)step * 4 + 0] = flow_now();
+        if (tracer) f.trace[(size_t)step * 16 + 0] = flow_now();
         if (tid < nmy && tid < STEP_MAX_RUNS) s_chunk[tid] = step_chunk_of(start, bi + tid * B, p0, np, S, d.nb, 1);
         __syncthreads();
         if (tid == 0) {
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_flow_kernel(const __grid_co
                 const i64 rep_stride = (i64)d.nimg * d.npart * ih * iw * cp0;
                 float *out = const_cast<float *>(d.L[0].in);
                 const unsigned *words = f.symw + (size_t)img * f.rows_cap;
-                const unsigned tag = (unsigned)step;               // (step - 1) + 1
+                const unsigned tag = 0x800000u | ((f.tag_salt & 0x7fu) << 16) | ((unsigned)step & 0xffffu);      // step = (decoded step) + 1
                 for (int base = 0; base < pcount; base += 4 * STEP_THREADS) {
                     unsigned w[4];
 #pragma unroll
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_flow_kernel(const __grid_co
             }
             return;
         }
-        if (tracer) f.trace[(size_t)step * 4 + 1] = flow_now();
+        if (tracer) f.trace[(size_t)step * 16 + 1] = flow_now();
 
         // ---- the masked layers: no barrier between them, consumers poll the scalars they need (step_conv_phase<GI, true>)
         int it = 0;
@@ -242,9 +243,10 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_flow_kernel(const __grid_co
                 if (d.L[L].gi == 1) step_conv_phase<1, true>(d, d.L[L], step, ch, start, ws, wstride, s_tap, s_cell, cbase, img, &ctl);
                 else step_conv_phase<3, true>(d, d.L[L], step, ch, start, ws, wstride, s_tap, s_cell, cbase, img, &ctl);
             }
+            if (tracer && L < 12) f.trace[(size_t)step * 16 + 2 + L] = flow_now();
         }
         cp_async_wait<0>();
-        if (tracer) f.trace[(size_t)step * 4 + 2] = flow_now();
+        if (tracer) f.trace[(size_t)step * 16 + 14] = flow_now();
 
         // ---- DExtract2Batch + GMM table: row k of the image's window, one 16-byte store to the host per row
         if (count > 0) {
@@ -268,12 +270,12 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_flow_kernel(const __grid_co
                 r.x = (unsigned)(int)c[1] | ((unsigned)(int)c[2] << 16);
                 r.y = (unsigned)(int)c[3] | ((unsigned)(int)c[4] << 16);
                 r.z = (unsigned)(int)c[5] | ((unsigned)(int)c[6] << 16);
-                r.w = (unsigned)(int)c[7] | (((unsigned)(step + 1) & 0xffffu) << 16);
+                r.w = (unsigned)(int)c[7] | ((0x8000u | ((f.tag_salt + (unsigned)step) & 0x7fffu)) << 16);
                 asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(rows + k), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w)
                              : "memory");
             }
         }
-        if (tracer) f.trace[(size_t)step * 4 + 3] = flow_now();
+        if (tracer) f.trace[(size_t)step * 16 + 15] = flow_now();
         __syncthreads();                               // the step's shared tables are rebuilt next
     }
 }
@@ -292,6 +294,7 @@ struct FlowState {                  // per device, created on first use, guarded
     unsigned *h_ctl = nullptr;      // mapped
     size_t rows_cap_total = 0;
     bool attr_set = false;
+    unsigned epoch = 1;
     int max_smem = 0;
 };
 std::mutex g_states_mu;
@@ -355,7 +358,7 @@ int pcx_wave_decode_flow(const pcx_wave_net &n, pcx_coder *const *coders, long l
     int B = n.nimg > 0 ? max_grid / n.nimg : 0;                  // blocks per image
     if (const char *e = getenv("PCX_FLOW_BLOCKS")) B = atoi(e) >= 2 && atoi(e) < B ? atoi(e) : B;      // debugging / tuning
     const int smax = getenv("PCX_FLOW_SMAX") ? atoi(getenv("PCX_FLOW_SMAX")) : 0;
-    if (per_sm < 1 || B < 2 || nsteps >= 65534) { *unsupported = true; return PCX_OK; }
+    if (per_sm < 1 || B < 2 || nsteps >= 32767) { *unsupported = true; return PCX_OK; }
 
     // ---- per-step schedule (per image): runs of at most S cells per (net, plane); block i of the image takes runs i, i + B, ...
     int maxcount = 1;
@@ -482,6 +485,8 @@ int pcx_wave_decode_flow(const pcx_wave_net &n, pcx_coder *const *coders, long l
     }
     PCX_CUDA(cudaMemsetAsync(n.layers[0].in, 0, sizeof(float) * (size_t)nrep * n.npart * n.G * (n.h + 2 * n.pad) * (n.W + 2 * n.pad), s));
     f.nsteps = nsteps; f.rows_cap = rows_cap; f.blocks_per_img = B;
+    const unsigned salt = (st.epoch++ * 9973u) & 0x7fffu;
+    f.tag_salt = salt;
     f.start = st.d_start; f.sched = st.d_sched; f.dev_ctl = st.dev_ctl;
     f.timeout_ns = 20ull * 1000000000ull;
     if (const char *e = getenv("PCX_FLOW_TIMEOUT_MS")) f.timeout_ns = (unsigned long long)atoll(e) * 1000000ull;
@@ -489,8 +494,8 @@ int pcx_wave_decode_flow(const pcx_wave_net &n, pcx_coder *const *coders, long l
     const char *trace_path = getenv("PCX_WAVE_TRACE");
     unsigned long long *h_trace = nullptr;
     if (trace_path) {
-        if (cudaHostAlloc((void **)&h_trace, sizeof(unsigned long long) * 4 * (size_t)(nsteps + 1), cudaHostAllocMapped) == cudaSuccess) {
-            memset(h_trace, 0, sizeof(unsigned long long) * 4 * (size_t)(nsteps + 1));
+        if (cudaHostAlloc((void **)&h_trace, sizeof(unsigned long long) * 16 * (size_t)(nsteps + 1), cudaHostAllocMapped) == cudaSuccess) {
+            memset(h_trace, 0, sizeof(unsigned long long) * 16 * (size_t)(nsteps + 1));
             if (cudaHostGetDevicePointer((void **)&f.trace, h_trace, 0) != cudaSuccess) f.trace = nullptr;
         } else {
             (void)cudaGetLastError();
@@ -544,8 +549,9 @@ int pcx_wave_decode_flow(const pcx_wave_net &n, pcx_coder *const *coders, long l
                     memcpy(snap.data(), st.h_rows + base, sizeof(uint4) * (size_t)(cnt - m.pos));
                     src = reinterpret_cast<const uint16_t *>(snap.data());
                 }
-                const int rc = pcx_coder_decodes_rows16(coders[i], src, cnt - m.pos, (unsigned)(m.step + 1) & 0xffffu,
-                                                        (unsigned)(m.step + 1), st.h_symw + base, &got);
+                const int rc = pcx_coder_decodes_rows16(coders[i], src, cnt - m.pos, 0x8000u | ((salt + (unsigned)m.step) & 0x7fffu),
+                                                        0x800000u | ((salt & 0x7fu) << 16) | ((unsigned)(m.step + 1) & 0xffffu),
+                                                        st.h_symw + base, &got);
                 if (dump && got > 0) {                  // kept in memory, written after the decode: the host must stay fast
                     for (int r = 0; r < got; r++) {
                         uint4 rec = snap[(size_t)r];
@@ -600,11 +606,16 @@ int pcx_wave_decode_flow(const pcx_wave_net &n, pcx_coder *const *coders, long l
     const unsigned dev_err = h_ctl[1];
     if (h_trace) {
         if (FILE *fp = fopen(trace_path, "w")) {
-            fprintf(fp, "# step rows | image 0 leader block, ns: tables+dinput wait, layers, gmm rows, (host + wait) until next step\n");
+            fprintf(fp, "# step rows | image 0 leader block, ns: tables + wait for symbols | after each layer | gmm rows | until next step\n");
             for (int stp_ = 0; stp_ < nsteps; stp_++) {
-                const unsigned long long *t = h_trace + (size_t)stp_ * 4;
-                fprintf(fp, "%d %d | %lld %lld %lld %lld\n", stp_, counts[stp_], (long long)(t[1] - t[0]), (long long)(t[2] - t[1]),
-                        (long long)(t[3] - t[2]), (long long)(t[4] - t[3]));
+                const unsigned long long *t = h_trace + (size_t)stp_ * 16;
+                fprintf(fp, "%d %d | %lld |", stp_, counts[stp_], (long long)(t[1] - t[0]));
+                unsigned long long prev = t[1];
+                for (int L = 0; L < 12 && L < n.nlayers; L++) {
+                    fprintf(fp, " %lld", (long long)(t[2 + L] - prev));
+                    prev = t[2 + L];
+                }
+                fprintf(fp, " | %lld %lld | layers %lld\n", (long long)(t[15] - t[14]), (long long)(t[16] - t[15]), (long long)(t[14] - t[1]));
             }
             fclose(fp);
         }
