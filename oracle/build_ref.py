@@ -8,6 +8,11 @@ Outputs (git-ignored, but they travel to the GPU box with the gpurun snapshot):
                               nvcc defaults (-fmad=true), only -std=c++17 and the gencode differ
                               from the reference's setup.py:10-17.
   oracle/_ref/coder_ref.so  - the reference host arithmetic coder (coder/*.cpp).
+  oracle/_ref/refpy/        - the reference's Python layer (PCONV_operator/, model_zoo_v2, pseudo_codec) as sourceless byte
+                              code (.pyc), compiled from where it lies: tests/test_gpu_reference_python.py runs the reference's
+                              own PseudoEncoder / PseudoDecoder on the GPU box against (a) the unmodified PCONV_ref / coder_ref
+                              extensions - the real reference end to end - and (b) this repository's `PCONV` / `coder` mirrors
+                              (INTEGRATION.md route A).
 
 The sources are compiled where they lie; no reference source is copied into this repository.
 The modules are renamed through -DTORCH_EXTENSION_NAME so they can be imported next to the
@@ -31,7 +36,23 @@ EXT_SOURCES = [
 CODER_SOURCES = ["python.cpp", "ArithmeticCoder.cpp", "BitIoStream.cpp"]
 
 
-def build(which=("coder", "pconv"), verbose=False):
+PY_MODULES = ["model_zoo_v2.py", "pseudo_codec.py"]
+
+
+def build_refpy():
+    """byte-compile the reference's Python layer into oracle/_ref/refpy (no source is copied)"""
+    import py_compile
+    dst = os.path.join(OUT, "refpy")
+    os.makedirs(os.path.join(dst, "PCONV_operator"), exist_ok=True)
+    pairs = [(os.path.join(REF, m), os.path.join(dst, m + "c")) for m in PY_MODULES]
+    opdir = os.path.join(REF, "PCONV_operator")
+    pairs += [(os.path.join(opdir, f), os.path.join(dst, "PCONV_operator", f + "c")) for f in sorted(os.listdir(opdir)) if f.endswith(".py")]
+    for src, out in pairs:
+        py_compile.compile(src, cfile=out, dfile=os.path.relpath(src, REF), doraise=True)
+    print(f"[build_ref] {dst} ({len(pairs)} modules)")
+
+
+def build(which=("coder", "pconv", "py"), verbose=False):
     if not os.path.isdir(REF):
         print(f"[build_ref] {REF} not present - keeping whatever is prebuilt in {OUT}")
         return False
@@ -44,6 +65,8 @@ def build(which=("coder", "pconv"), verbose=False):
     os.environ.setdefault("MAX_JOBS", str(os.cpu_count() or 4))
     from torch.utils import cpp_extension as ce
     os.makedirs(OUT, exist_ok=True)
+    if "py" in which:
+        build_refpy()
     if "coder" in which:
         bd = os.path.join(OUT, "build_coder")
         os.makedirs(bd, exist_ok=True)
@@ -73,5 +96,5 @@ def _publish(build_dir, name):
 
 
 if __name__ == "__main__":
-    which = tuple(sys.argv[1:]) or ("coder", "pconv")
+    which = tuple(sys.argv[1:]) or ("coder", "pconv", "py")
     build(which, verbose=True)

@@ -60,6 +60,26 @@ static inline int ceil_div(i64 a, i64 b) { return (int)((a + b - 1) / b); }
 
 int pcx_sm_count();
 
+// "first call on this device": function attributes (dynamic shared memory limits, occupancy figures) are per device, and the
+// reference API allows several devices in one process.  PCX_ONCE_PER_DEVICE(flag) { ... } runs its body once for every device
+// it is reached on; `flag` is a function-local static PcxDeviceOnce.  The body runs under the flag's mutex, so a second host
+// thread cannot launch before the attribute is set.
+#include <mutex>
+struct PcxDeviceOnce {
+    std::mutex mu;
+    unsigned long long done = 0;
+    int slot[64] = {};                       // a per-device value computed by the body (e.g. an occupancy figure)
+};
+static inline int pcx_current_device()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    return dev;
+}
+#define PCX_ONCE_PER_DEVICE(flag)                                                                     \
+    for (struct { std::unique_lock<std::mutex> lk; int dev; bool go; } o__ = {std::unique_lock<std::mutex>((flag).mu), pcx_current_device(), true}; \
+         o__.go && !(((flag).done >> o__.dev) & 1ull); (flag).done |= 1ull << o__.dev, o__.go = false)
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

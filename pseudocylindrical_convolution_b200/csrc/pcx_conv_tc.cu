@@ -886,11 +886,8 @@ static int launch_tc_v(const CUtensorMap &mx, const CUtensorMap &mw, const TcPar
                      const float *mul, const float *residual, float *y, cudaStream_t s)
 {
     using C = Cfg<NT>;
-    static bool attr = false;
-    if (!attr) {
-        PCX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT, ACTK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        attr = true;
-    }
+    static PcxDeviceOnce once;
+    PCX_ONCE_PER_DEVICE(once) PCX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT, ACTK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     long long grid = p.total_tiles < pcx_sm_count() ? p.total_tiles : pcx_sm_count();
     conv_tc_kernel<NT, ACTK><<<(unsigned)grid, TC_THREADS, C::SMEM, s>>>(mx, mw, p, bias, slope, mul, residual, y);
     PCX_LAUNCHED();
@@ -903,8 +900,8 @@ static int launch_pair_v(const CUtensorMap &mx, const CUtensorMap &mw, const TcP
                        const float *mul, const float *residual, float *y, cudaStream_t s)
 {
     using C = Cfg2<NT>;
-    static int max_clusters = 0;
-    if (max_clusters == 0) {
+    static PcxDeviceOnce once;
+    PCX_ONCE_PER_DEVICE(once) {
         PCX_CUDA(cudaFuncSetAttribute(conv_pair_kernel<NT, ACTK, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(pcx_sm_count() / 2 * 2);
@@ -913,8 +910,9 @@ static int launch_pair_v(const CUtensorMap &mx, const CUtensorMap &mw, const TcP
         int n = 0;
         cudaError_t e = cudaOccupancyMaxActiveClusters(&n, conv_pair_kernel<NT, ACTK, DBG>, &cfg);
         if (e != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = pcx_sm_count() / 2; }
-        max_clusters = n;
+        once.slot[pcx_current_device()] = n;
     }
+    const int max_clusters = once.slot[pcx_current_device()];
     long long clusters = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;
     conv_pair_kernel<NT, ACTK, DBG><<<(unsigned)(2 * clusters), NUM_THREADS, C::SMEM, s>>>(mx, mw, p, bias, slope, mul, residual, y);
     PCX_LAUNCHED();

@@ -11,6 +11,8 @@
 #include <stdlib.h>
 #include <atomic>
 #include <thread>
+#include <mutex>
+#include <condition_variable>
 #include <chrono>
 #include <string.h>
 #include <math.h>
@@ -1010,15 +1012,41 @@ struct PinnedPool {
     float *d_prev = nullptr;
     size_t rows = 0;
 };
-PinnedPool g_pin;
+// Everything the engines keep between calls lives in one record PER DEVICE (the reference API allows several devices in one
+// process: every op carries its `device`, pseudo_codec has --gpu-id), guarded by a mutex held for the duration of an
+// encode / decode call - two host threads on one device take turns, two devices do not touch each other's buffers.
+struct WaveDev {
+    std::mutex mu;
+    PinnedPool pin;
+    unsigned *bar = nullptr;                 // grid barrier counter of the step kernel
+    float *step_scratch = nullptr;           // channels-last scratch of the step kernel (+ cell table)
+    size_t step_scratch_bytes = 0;
+    int *d_start = nullptr;                  // device copy of the plane prefix
+    size_t d_start_cap = 0;
+    cudaStream_t s_copy = nullptr;           // one-shot encoder: CDF rows leave on their own stream
+    cudaEvent_t slab_ev[16] = {};
+};
+std::mutex g_wave_devs_mu;
+WaveDev *g_wave_devs[64] = {nullptr};
+
+WaveDev *wave_dev()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(g_wave_devs_mu);
+    if (!g_wave_devs[dev]) g_wave_devs[dev] = new WaveDev();
+    return g_wave_devs[dev];
+}
 
 
-// Per-image host coding in parallel: the nimg bitstreams are independent, so every wavefront step hands image i's rows to
-// worker i (the calling thread takes image 0).  Workers spin on a generation counter - a step's coding job is tens of
-// microseconds, far below a condition variable's wake-up latency - and live only for the duration of one encode / decode.
+// Per-image host coding in parallel: the nimg bitstreams are independent.  T = pcx_host_coder_threads(nimg) threads (the caller
+// is thread 0) share the images round-robin, so a rank never runs more coder threads than its share of the host cores - eight
+// ranks x eight images used to be 64 spinning threads on a 32-core box and decode throughput collapsed at N = 8.  Workers
+// spin briefly on a generation counter (a step's coding job is tens of microseconds, below a condition variable's wake-up
+// latency), then block on a condition variable; the caller waits the same way.  The pool lives for one encode / decode.
 struct CoderPool {
     pcx_coder *const *coders = nullptr;
-    int nimg = 1, ncode = 8;
+    int nimg = 1, ncode = 8, nthreads = 1;
     bool encode = true;
     // job of the current generation
     const int32_t *cdf = nullptr;
@@ -1027,60 +1055,84 @@ struct CoderPool {
     int per = 0;
     std::atomic<int> gen{0}, done{0}, status{0};
     std::atomic<bool> quit{false};
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
     std::vector<std::thread> threads;
 
-    void work(int im)
+    void work(int t)
     {
-        int rc;
-        if (encode) rc = pcx_coder_encodes(coders[im], cdf + (size_t)im * per * (ncode + 1), ncode, lab_i + (size_t)im * per, per);
-        else rc = pcx_coder_decodes(coders[im], cdf + (size_t)im * per * (ncode + 1), ncode, per, lab_f + (size_t)im * per);
-        if (rc < 0) status.store(rc);
+        for (int im = t; im < nimg; im += nthreads) {
+            int rc;
+            if (encode) rc = pcx_coder_encodes(coders[im], cdf + (size_t)im * per * (ncode + 1), ncode, lab_i + (size_t)im * per, per);
+            else rc = pcx_coder_decodes(coders[im], cdf + (size_t)im * per * (ncode + 1), ncode, per, lab_f + (size_t)im * per);
+            if (rc < 0) status.store(rc);
+        }
     }
-    void loop(int im)
+    void loop(int t)
     {
         int seen = 0;
         for (;;) {
             int spins = 0;
-            while (gen.load(std::memory_order_acquire) == seen && !quit.load(std::memory_order_relaxed))
-                if (++spins > 2000) std::this_thread::yield();
+            while (gen.load(std::memory_order_acquire) == seen && !quit.load(std::memory_order_relaxed)) {
+                if (++spins < 4000) { __builtin_ia32_pause(); continue; }
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [&] { return gen.load(std::memory_order_acquire) != seen || quit.load(); });
+            }
             if (quit.load()) return;
             seen = gen.load(std::memory_order_acquire);
-            work(im);
-            done.fetch_add(1, std::memory_order_release);
+            work(t);
+            if (done.fetch_add(1, std::memory_order_acq_rel) + 1 == nthreads - 1) {
+                std::lock_guard<std::mutex> lk(mu);
+                cv_done.notify_one();
+            }
         }
     }
     void start(pcx_coder *const *c, int n, int nc, bool enc)
     {
         coders = c; nimg = n; ncode = nc; encode = enc;
-        for (int im = 1; im < nimg; im++) threads.emplace_back([this, im] { loop(im); });
+        nthreads = pcx_host_coder_threads(nimg);
+        for (int t = 1; t < nthreads; t++) threads.emplace_back([this, t] { loop(t); });
     }
     int run(const int32_t *cdf_, int32_t *li, float *lf, int per_)
     {
         cdf = cdf_; lab_i = li; lab_f = lf; per = per_;
         done.store(0, std::memory_order_relaxed);
-        gen.fetch_add(1, std::memory_order_release);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            gen.fetch_add(1, std::memory_order_release);
+        }
+        cv_work.notify_all();
         work(0);
-        while (done.load(std::memory_order_acquire) < nimg - 1) { }
+        int spins = 0;
+        while (done.load(std::memory_order_acquire) < nthreads - 1) {
+            if (++spins < 4000) { __builtin_ia32_pause(); continue; }
+            std::unique_lock<std::mutex> lk(mu);
+            cv_done.wait(lk, [&] { return done.load(std::memory_order_acquire) >= nthreads - 1; });
+        }
         return status.load();
     }
     ~CoderPool()
     {
-        quit.store(true);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit.store(true);
+        }
+        cv_work.notify_all();
         for (auto &t : threads) t.join();
     }
 };
 
-int ensure_pinned(size_t rows, int nstep)
+int ensure_pinned(WaveDev &D, size_t rows, int nstep)
 {
-    if (rows <= g_pin.rows) return PCX_OK;
+    if (rows <= D.pin.rows) return PCX_OK;
     for (int i = 0; i < 2; i++) {
-        if (g_pin.cdf[i]) cudaFreeHost(g_pin.cdf[i]);
-        if (g_pin.lab[i]) cudaFreeHost(g_pin.lab[i]);
+        if (D.pin.cdf[i]) cudaFreeHost(D.pin.cdf[i]);
+        if (D.pin.lab[i]) cudaFreeHost(D.pin.lab[i]);
         // mapped: the fused decoder step writes CDF rows / reads symbols through these buffers directly (zero-copy)
-        PCX_CUDA(cudaHostAlloc((void **)&g_pin.cdf[i], rows * (nstep + 1) * sizeof(int32_t), cudaHostAllocMapped | cudaHostAllocPortable));
-        PCX_CUDA(cudaHostAlloc((void **)&g_pin.lab[i], rows * sizeof(float), cudaHostAllocMapped | cudaHostAllocPortable));
+        PCX_CUDA(cudaHostAlloc((void **)&D.pin.cdf[i], rows * (nstep + 1) * sizeof(int32_t), cudaHostAllocMapped | cudaHostAllocPortable));
+        PCX_CUDA(cudaHostAlloc((void **)&D.pin.lab[i], rows * sizeof(float), cudaHostAllocMapped | cudaHostAllocPortable));
     }
-    g_pin.rows = rows;
+    D.pin.rows = rows;
     return PCX_OK;
 }
 
@@ -1142,9 +1194,13 @@ int pcx_wave_encode(const pcx_wave_net *net, const float *d_data, pcx_coder *con
     for (int i = 0; i < net->nimg; i++) PCX_REQUIRE(coders[i] != nullptr, "null coder for image %d", i);
     const pcx_wave_net &n = *net;
     cudaStream_t s = (cudaStream_t)stream;
+    WaveDev *Dp = wave_dev();
+    PCX_REQUIRE(Dp != nullptr, "no current CUDA device");
+    WaveDev &D = *Dp;
+    std::lock_guard<std::mutex> dev_lock(D.mu);
     const int Hf = n.h * n.npart, nsteps = pcx_wave_steps(net);
     const size_t max_rows = (size_t)n.nimg * (size_t)(Hf < n.W ? Hf : n.W) * n.G + 16;
-    rc = ensure_pinned(max_rows, n.nstep);
+    rc = ensure_pinned(D, max_rows, n.nstep);
     if (rc < 0) return rc;
     cudaEvent_t ev[2];
     for (auto &e : ev) PCX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1166,8 +1222,8 @@ int pcx_wave_encode(const pcx_wave_net *net, const float *d_data, pcx_coder *con
             if (status < 0) break;
             counts[b] = cnt;
             if (cnt > 0) {
-                PCX_CUDA(cudaMemcpyAsync(g_pin.cdf[b], n.d_cdf, sizeof(int32_t) * (size_t)cnt * (n.nstep + 1), cudaMemcpyDeviceToHost, s));
-                PCX_CUDA(cudaMemcpyAsync(g_pin.lab[b], n.d_prev, sizeof(float) * (size_t)cnt, cudaMemcpyDeviceToHost, s));
+                PCX_CUDA(cudaMemcpyAsync(D.pin.cdf[b], n.d_cdf, sizeof(int32_t) * (size_t)cnt * (n.nstep + 1), cudaMemcpyDeviceToHost, s));
+                PCX_CUDA(cudaMemcpyAsync(D.pin.lab[b], n.d_prev, sizeof(float) * (size_t)cnt, cudaMemcpyDeviceToHost, s));
             }
             PCX_CUDA(cudaEventRecord(ev[b], s));
         }
@@ -1176,10 +1232,10 @@ int pcx_wave_encode(const pcx_wave_net *net, const float *d_data, pcx_coder *con
             PCX_CUDA(cudaEventSynchronize(ev[pb]));
             const int cnt = counts[pb];
             if (cnt > 0) {
-                int32_t *lab = reinterpret_cast<int32_t *>(g_pin.lab[pb]);
-                for (int i = 0; i < cnt; i++) lab[i] = (int32_t)g_pin.lab[pb][i];            // symbols 0..7 stored as float
+                int32_t *lab = reinterpret_cast<int32_t *>(D.pin.lab[pb]);
+                for (int i = 0; i < cnt; i++) lab[i] = (int32_t)D.pin.lab[pb][i];            // symbols 0..7 stored as float
                 // rows are ordered (image, cell of the window): every image has its own bitstream and its own host thread
-                status = pool.run(g_pin.cdf[pb], lab, nullptr, cnt / n.nimg);
+                status = pool.run(D.pin.cdf[pb], lab, nullptr, cnt / n.nimg);
                 total += cnt;
             }
         }
@@ -1232,7 +1288,11 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
     wfirst[nsteps] = 0;
     const int cap = n.cdf_rows / n.nimg;                      // rows per image per chunk
     PCX_REQUIRE(cap >= maxcnt, "cdf_rows %d too small for a step of %d rows x %d images", n.cdf_rows, maxcnt, n.nimg);
-    rc = ensure_pinned((size_t)n.cdf_rows, n.nstep);
+    WaveDev *Dp = wave_dev();
+    PCX_REQUIRE(Dp != nullptr, "no current CUDA device");
+    WaveDev &D = *Dp;
+    std::lock_guard<std::mutex> dev_lock(D.mu);
+    rc = ensure_pinned(D, (size_t)n.cdf_rows, n.nstep);
     if (rc < 0) return rc;
     PCX_CUDA(cudaMemcpyAsync(n.d_steptab, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, s));
 
@@ -1271,12 +1331,12 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
         while (st < nsteps && (rowbase[st] < target || st <= (k ? slab_end[k - 1] : 0))) st++;
         slab_end[k] = k == nslab - 1 ? nsteps : st;
     }
-    static cudaStream_t s_copy = nullptr;                        // CDF rows leave on their own stream, next to the next slab
-    static cudaEvent_t slab_ev[16];
-    if (!s_copy) {
-        PCX_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
-        for (auto &e : slab_ev) PCX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (!D.s_copy) {                                             // CDF rows leave on their own stream, next to the next slab
+        PCX_CUDA(cudaStreamCreateWithFlags(&D.s_copy, cudaStreamNonBlocking));
+        for (auto &e : D.slab_ev) PCX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
+    cudaStream_t s_copy = D.s_copy;
+    cudaEvent_t *slab_ev = D.slab_ev;
     for (int L = 0; L < n.nlayers; L++) {
         const pcx_wave_layer &l = n.layers[L];
         const i64 out_elems = (i64)nrep * n.npart * n.G * l.go * (n.h + 2 * l.pad_out) * (n.W + 2 * l.pad_out);
@@ -1324,11 +1384,14 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
         if (!no_smem_form && g_opt_smem.load() != 0 && l.go == 3 && n.W % (32 * CT_CPT) == 0 && (l.gi == 1 || l.gi == 3) && n.pad == 2 && cs_bytes <= 220 * 1024 &&
             (i64)nrep * tsplit <= 65535) {
             // shared-memory form: the block stages its 5x5 input window once and loops over the channel groups
-            static int unroll = 0;
-            if (unroll == 0) {
+            // measured at 2048x4096 (ms per layer): x1 1.00, x2 1.12, runtime tree 1.25-1.42, full unroll 2.53
+            static const int unroll = [] {
                 const char *e = getenv("PCX_CTX_UNROLL");
-                unroll = e ? atoi(e) : 1;       // measured at 2048x4096 (ms per layer): x1 1.00, x2 1.12, runtime tree 1.25-1.42, full unroll 2.53
-                if (unroll != 2 && unroll != 8 && unroll != 9) unroll = 1;
+                const int u = e ? atoi(e) : 1;
+                return (u == 2 || u == 8 || u == 9) ? u : 1;
+            }();
+            static PcxDeviceOnce cs_once;
+            PCX_ONCE_PER_DEVICE(cs_once) {
                 PCX_CUDA(cudaFuncSetAttribute(ctx_conv_smem_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
                 PCX_CUDA(cudaFuncSetAttribute(ctx_conv_smem_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
                 PCX_CUDA(cudaFuncSetAttribute(ctx_conv_smem_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -1412,7 +1475,7 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
         if (e != cudaSuccess) { pcx_set_error("cudaEventSynchronize -> %s", cudaGetErrorString(e)); return PCX_ECUDA; }
         if (per_chunk[b] <= 0) return PCX_OK;
         total_rows += (long long)per_chunk[b] * n.nimg;
-        return pool.run(g_pin.cdf[b], reinterpret_cast<int32_t *>(g_pin.lab[b]), nullptr, per_chunk[b]);
+        return pool.run(D.pin.cdf[b], reinterpret_cast<int32_t *>(D.pin.lab[b]), nullptr, per_chunk[b]);
     };
     int cur_slab = 0;
     while (s0 < nsteps && status == PCX_OK) {
@@ -1429,8 +1492,8 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
                                                                         s0, s1, n.nimg, n.npart, n.G, last.go, n.h, n.W, n.ng, n.nstep,
                                                                         n.gmm_bias, n.gmm_total, n.gmm_beta, n.d_cdf, n.d_lab);
             PCX_LAUNCHED();
-            PCX_CUDA(cudaMemcpyAsync(g_pin.cdf[b], n.d_cdf, sizeof(int32_t) * (size_t)rows * (n.nstep + 1), cudaMemcpyDeviceToHost, s_copy));
-            PCX_CUDA(cudaMemcpyAsync(g_pin.lab[b], n.d_lab, sizeof(int32_t) * (size_t)rows, cudaMemcpyDeviceToHost, s_copy));
+            PCX_CUDA(cudaMemcpyAsync(D.pin.cdf[b], n.d_cdf, sizeof(int32_t) * (size_t)rows * (n.nstep + 1), cudaMemcpyDeviceToHost, s_copy));
+            PCX_CUDA(cudaMemcpyAsync(D.pin.lab[b], n.d_lab, sizeof(int32_t) * (size_t)rows, cudaMemcpyDeviceToHost, s_copy));
         }
         PCX_CUDA(cudaEventRecord(ev[b], s_copy));
         if (chunk >= 1) status = code_chunk(b ^ 1);           // code chunk c-1 while chunk c is computed and copied
@@ -1450,9 +1513,6 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
 }
 
 static std::atomic<int> g_wave_fused{2};
-static unsigned *g_bar = nullptr;
-static float *g_step_scratch = nullptr;
-static size_t g_step_scratch_bytes = 0;
 
 int pcx_wave_set_fused(int on)
 {
@@ -1465,10 +1525,14 @@ static int wave_decode_fused(const pcx_wave_net &n, pcx_coder *const *coders, lo
 {
     const int Hf = n.h * n.npart, nsteps = pcx_wave_steps(&n), nrep = n.nb * n.nimg;
     const size_t max_rows = (size_t)n.nimg * (size_t)(Hf < n.W ? Hf : n.W) * n.G + 16;
-    int rc = ensure_pinned(max_rows, n.nstep);
+    WaveDev *Dp = wave_dev();
+    PCX_REQUIRE(Dp != nullptr, "no current CUDA device");
+    WaveDev &D = *Dp;
+    std::lock_guard<std::mutex> dev_lock(D.mu);
+    int rc = ensure_pinned(D, max_rows, n.nstep);
     if (rc < 0) return rc;
-    if (g_bar == nullptr) PCX_CUDA(cudaMalloc((void **)&g_bar, 64));
-    PCX_CUDA(cudaMemsetAsync(g_bar, 0, 64, s));
+    if (D.bar == nullptr) PCX_CUDA(cudaMalloc((void **)&D.bar, 64));
+    PCX_CUDA(cudaMemsetAsync(D.bar, 0, 64, s));
     StepNet d;
     d.nlayers = n.nlayers; d.nb = n.nb; d.nimg = n.nimg; d.npart = n.npart; d.G = n.G; d.h = n.h; d.W = n.W; d.pad = n.pad;
     d.nstep = n.nstep; d.ng = n.ng;
@@ -1477,12 +1541,16 @@ static int wave_decode_fused(const pcx_wave_net &n, pcx_coder *const *coders, lo
     d.hband = n.d_band; d.hrow = n.d_row; d.hcol = n.d_col; d.htw = n.d_tw; d.order = n.d_order;
     float *dev_prev = nullptr;
     int *dev_cdf = nullptr;
-    PCX_CUDA(cudaHostGetDevicePointer((void **)&dev_prev, g_pin.lab[0], 0));
-    PCX_CUDA(cudaHostGetDevicePointer((void **)&dev_cdf, g_pin.cdf[0], 0));
-    d.prev = dev_prev; d.cdf = dev_cdf; d.bar = g_bar;
+    PCX_CUDA(cudaHostGetDevicePointer((void **)&dev_prev, D.pin.lab[0], 0));
+    PCX_CUDA(cudaHostGetDevicePointer((void **)&dev_cdf, D.pin.cdf[0], 0));
+    d.prev = dev_prev; d.cdf = dev_cdf; d.bar = D.bar;
     // PCX_WAVE_TRACE=<file>: per-step device timestamps (block 0) + host wall clock of the loop, written as text
     const char *trace_path = getenv("PCX_WAVE_TRACE");
     unsigned long long *h_dbg = nullptr;
+    struct HostGuard {                           // the trace buffer is released on every exit path
+        unsigned long long **p;
+        ~HostGuard() { if (*p) cudaFreeHost(*p); }
+    } dbg_guard{&h_dbg};
     std::vector<double> host_us;
     d.dbg = nullptr;
     if (trace_path) {
@@ -1503,24 +1571,24 @@ static int wave_decode_fused(const pcx_wave_net &n, pcx_coder *const *coders, lo
     const int ncell_total = n.h_start[Hf + n.W - 1];                              // valid cells of one image
     const size_t cell_off = (sizeof(float) * (size_t)off[n.nlayers + 1] + 255) / 256 * 256;
     const size_t need_bytes = cell_off + sizeof(int4) * (size_t)ncell_total + 256;
-    if (need_bytes > g_step_scratch_bytes) {
-        if (g_step_scratch) cudaFree(g_step_scratch);
-        g_step_scratch = nullptr;
-        g_step_scratch_bytes = 0;
-        PCX_CUDA(cudaMalloc((void **)&g_step_scratch, need_bytes));
-        g_step_scratch_bytes = need_bytes;
+    if (need_bytes > D.step_scratch_bytes) {
+        if (D.step_scratch) cudaFree(D.step_scratch);
+        D.step_scratch = nullptr;
+        D.step_scratch_bytes = 0;
+        PCX_CUDA(cudaMalloc((void **)&D.step_scratch, need_bytes));
+        D.step_scratch_bytes = need_bytes;
     }
-    PCX_CUDA(cudaMemsetAsync(g_step_scratch, 0, need_bytes, s));
+    PCX_CUDA(cudaMemsetAsync(D.step_scratch, 0, need_bytes, s));
     for (int L = 0; L < n.nlayers; L++) {
         const pcx_wave_layer &l = n.layers[L];
         StepLayer &sl = d.L[L];
         sl.weight = l.weight; sl.bias = l.bias; sl.act = l.act;
-        sl.in = g_step_scratch + off[L];
-        sl.out = g_step_scratch + off[L + 1];
+        sl.in = D.step_scratch + off[L];
+        sl.out = D.step_scratch + off[L + 1];
         sl.add = nullptr;
         if (l.add) {
             for (int M = 0; M < L; M++)
-                if (n.layers[M].out == l.add) sl.add = g_step_scratch + off[M + 1];
+                if (n.layers[M].out == l.add) sl.add = D.step_scratch + off[M + 1];
             PCX_REQUIRE(sl.add != nullptr, "layer %d: the residual source must be the output of an earlier layer", L);
             PCX_REQUIRE(n.layers[L].pad_out == n.pad, "layer %d: residual add on an unpadded output", L);
         }
@@ -1530,7 +1598,7 @@ static int wave_decode_fused(const pcx_wave_net &n, pcx_coder *const *coders, lo
                     "layer %d must read the padded output of layer %d", L, L - 1);
     }
     d.sym_nchw = n.layers[0].in;
-    int4 *d_cell = reinterpret_cast<int4 *>(reinterpret_cast<char *>(g_step_scratch) + cell_off);
+    int4 *d_cell = reinterpret_cast<int4 *>(reinterpret_cast<char *>(D.step_scratch) + cell_off);
     step_cellinfo_kernel<<<ceil_div(ncell_total, 256), 256, 0, s>>>(n.d_order, d_cell, ncell_total, n.h, n.W);
     PCX_LAUNCHED();
     d.cell = d_cell;
@@ -1549,8 +1617,14 @@ static int wave_decode_fused(const pcx_wave_net &n, pcx_coder *const *coders, lo
     PCX_REQUIRE(per_sm >= 1, "wave_step_kernel does not fit on an SM");
     const int max_grid = pcx_sm_count() * per_sm;
     const int nplanes = Hf + n.W - 1;
-    int *d_start = nullptr;
-    PCX_CUDA(cudaMalloc((void **)&d_start, sizeof(int) * (size_t)(Hf + n.W)));
+    if ((size_t)(Hf + n.W) > D.d_start_cap) {               // cached: no allocation (and no leak on an early return) per call
+        if (D.d_start) cudaFree(D.d_start);
+        D.d_start = nullptr;
+        D.d_start_cap = 0;
+        PCX_CUDA(cudaMalloc((void **)&D.d_start, sizeof(int) * (size_t)(Hf + n.W)));
+        D.d_start_cap = (size_t)(Hf + n.W);
+    }
+    int *d_start = D.d_start;
     PCX_CUDA(cudaMemcpyAsync(d_start, n.h_start, sizeof(int) * (size_t)(Hf + n.W), cudaMemcpyHostToDevice, s));
 
     CoderPool pool;
@@ -1592,14 +1666,14 @@ static int wave_decode_fused(const pcx_wave_net &n, pcx_coder *const *coders, lo
         PCX_CUDA(cudaStreamSynchronize(s));
         auto t2 = std::chrono::steady_clock::now();
         if (count > 0) {
-            rc = pool.run(g_pin.cdf[0], nullptr, g_pin.lab[0], count);
+            rc = pool.run(D.pin.cdf[0], nullptr, D.pin.lab[0], count);
             if (dump) {                                 // PCX_WAVE_DUMP=<file>: same text as the dataflow engine writes (debugging)
                 for (int im = 0; im < n.nimg; im++)
                     for (int r = 0; r < count; r++) {
-                        const int32_t *row = g_pin.cdf[0] + ((size_t)im * count + r) * 9;
+                        const int32_t *row = D.pin.cdf[0] + ((size_t)im * count + r) * 9;
                         fprintf(dump, "%d %d %d |", im, step, r);
                         for (int j = 1; j < 8; j++) fprintf(dump, " %d", row[j]);
-                        fprintf(dump, " | %d\n", (int)g_pin.lab[0][(size_t)im * count + r]);
+                        fprintf(dump, " | %d\n", (int)D.pin.lab[0][(size_t)im * count + r]);
                     }
             }
             if (rc < 0) { if (dump) fclose(dump); return rc; }
@@ -1614,7 +1688,6 @@ static int wave_decode_fused(const pcx_wave_net &n, pcx_coder *const *coders, lo
         pfirst = first;
         pcount = count;
     }
-    cudaFree(d_start);
     if (dump) fclose(dump);
     // the last step's symbols never pass through the network: one more DInput2 (pseudo_codec.py:159)
     rc = pcx_dinput_step(dev_prev, n.layers[0].in, n.nimg, n.npart, n.G, n.h, n.W, n.pad, n.input_bias, n.nb, nsteps, n.d_order, n.h_start, s);
@@ -1634,6 +1707,7 @@ static int wave_decode_fused(const pcx_wave_net &n, pcx_coder *const *coders, lo
             fclose(f);
         }
         cudaFreeHost(h_dbg);
+        h_dbg = nullptr;
     }
     if (n_symbols) *n_symbols = total;
     return PCX_OK;
@@ -1659,7 +1733,11 @@ int pcx_wave_decode(const pcx_wave_net *net, pcx_coder *const *coders, long long
     }
     const int Hf = n.h * n.npart, nsteps = pcx_wave_steps(net);
     const size_t max_rows = (size_t)n.nimg * (size_t)(Hf < n.W ? Hf : n.W) * n.G + 16;
-    rc = ensure_pinned(max_rows, n.nstep);
+    WaveDev *Dp = wave_dev();
+    PCX_REQUIRE(Dp != nullptr, "no current CUDA device");
+    WaveDev &D = *Dp;
+    std::lock_guard<std::mutex> dev_lock(D.mu);
+    rc = ensure_pinned(D, max_rows, n.nstep);
     if (rc < 0) return rc;
     PCX_CUDA(cudaMemsetAsync(n.d_prev, 0, sizeof(float) * (size_t)n.nimg * Hf * n.W, s));
     long long total = 0;
@@ -1670,11 +1748,11 @@ int pcx_wave_decode(const pcx_wave_net *net, pcx_coder *const *coders, long long
         rc = wave_launch_step(n, step, n.d_prev, &cnt, s);
         if (rc < 0) return rc;
         if (cnt > 0) {
-            PCX_CUDA(cudaMemcpyAsync(g_pin.cdf[0], n.d_cdf, sizeof(int32_t) * (size_t)cnt * (n.nstep + 1), cudaMemcpyDeviceToHost, s));
+            PCX_CUDA(cudaMemcpyAsync(D.pin.cdf[0], n.d_cdf, sizeof(int32_t) * (size_t)cnt * (n.nstep + 1), cudaMemcpyDeviceToHost, s));
             PCX_CUDA(cudaStreamSynchronize(s));
-            rc = pool.run(g_pin.cdf[0], nullptr, g_pin.lab[0], cnt / n.nimg);
+            rc = pool.run(D.pin.cdf[0], nullptr, D.pin.lab[0], cnt / n.nimg);
             if (rc < 0) return rc;
-            PCX_CUDA(cudaMemcpyAsync(n.d_prev, g_pin.lab[0], sizeof(float) * (size_t)cnt, cudaMemcpyHostToDevice, s));
+            PCX_CUDA(cudaMemcpyAsync(n.d_prev, D.pin.lab[0], sizeof(float) * (size_t)cnt, cudaMemcpyHostToDevice, s));
             total += cnt;
         }
     }

@@ -255,11 +255,8 @@ int pcx_gdn_fwd(const float *d_x, const float *d_beta_eff, const float *d_gamma_
     i64 ntiles = (i64)((W + GPIX - 1) / GPIX) * h * N * npart;
     i64 blocks = ntiles < pcx_sm_count() ? ntiles : pcx_sm_count();
     size_t smem = (size_t)(192 * 192 + 192 * GPIX) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        PCX_CUDA(cudaFuncSetAttribute(gdn_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    static PcxDeviceOnce once;
+    PCX_ONCE_PER_DEVICE(once) PCX_CUDA(cudaFuncSetAttribute(gdn_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gdn_kernel<192><<<(unsigned)blocks, GTHREADS, smem, (cudaStream_t)stream>>>(d_x, d_beta_eff, d_gamma_eff, d_residual, d_y, b, h, W, inverse, ntiles);
     PCX_LAUNCHED();
     return PCX_OK;

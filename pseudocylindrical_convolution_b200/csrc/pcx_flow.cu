@@ -309,25 +309,32 @@ FlowState *flow_state()
     return g_states[dev];
 }
 
-std::atomic<int> g_flow_threads{0};   // host decoder threads per call (0 = automatic)
+std::atomic<int> g_flow_threads{0};   // host coder threads per call (0 = automatic)
 
-int flow_host_threads(int nimg)
+}  // namespace
+
+// Host coder threads for a call that codes nimg bitstreams: explicit setting (pcx_flow_set_threads / PCX_CODER_THREADS) or the
+// cores this process may use divided by the local ranks (torchrun exports LOCAL_WORLD_SIZE; one process per GPU shares the
+// host), minus one for the Python thread; never more than one per image.
+int pcx_host_coder_threads(int nimg)
 {
     int t = g_flow_threads.load();
     if (t <= 0) {
         if (const char *e = getenv("PCX_CODER_THREADS")) t = atoi(e);
     }
     if (t <= 0) {
-        // one process per GPU: the host cores are shared by the local ranks (torchrun exports LOCAL_WORLD_SIZE)
         int cores = (int)std::thread::hardware_concurrency();
         cpu_set_t set;
         if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
         int local = 1;
         if (const char *e = getenv("LOCAL_WORLD_SIZE")) local = atoi(e) > 0 ? atoi(e) : 1;
-        t = cores / local - 1;                 // leave a core per rank to the Python thread
+        t = cores / local - 1;
     }
     return t < 1 ? 1 : (t > nimg ? nimg : t);
 }
+
+namespace {
+inline int flow_host_threads(int nimg) { return pcx_host_coder_threads(nimg); }
 
 }  // namespace
 

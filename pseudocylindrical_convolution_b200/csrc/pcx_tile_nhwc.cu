@@ -820,21 +820,15 @@ int pcx_slice_pad_nhwc(const float *d_in, float *d_out, int N, int C, int H, int
     const bool aligned = W % 4 == 0 && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0;
     if (aligned && C % 4 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && !force_v1 && !force_tma) {
         constexpr int smem3 = 2 * S3_BUF * 4 + XB_MAX * (int)sizeof(ColRecipe);
-        static bool attr3 = false;
-        if (!attr3) {
-            PCX_CUDA(cudaFuncSetAttribute(slice_pad_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-            attr3 = true;
-        }
+        static PcxDeviceOnce once3;
+        PCX_ONCE_PER_DEVICE(once3) PCX_CUDA(cudaFuncSetAttribute(slice_pad_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
         const i64 n_super = (i64)(P.h + 2 * pad) * P.xtotal;
         PCX_REQUIRE(n_super < (1LL << 31), "grid too large");
         slice_pad_v3_kernel<<<(unsigned)n_super, S3_THREADS, smem3, (cudaStream_t)stream>>>(d_in, d_out, d_src, (const float4 *)d_wt, d_band,
                                                                                           d_row, d_col, d_tw, b, P);
     } else if (aligned && !force_v1) {
-        static bool attr = false;
-        if (!attr) {
-            PCX_CUDA(cudaFuncSetAttribute(slice_pad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM));
-            attr = true;
-        }
+        static PcxDeviceOnce once;
+        PCX_ONCE_PER_DEVICE(once) PCX_CUDA(cudaFuncSetAttribute(slice_pad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM));
         const i64 n_super = (i64)(P.h + 2 * pad) * P.xtotal;
         const i64 ctas = 2LL * pcx_sm_count();
         slice_pad_tma_kernel<<<(unsigned)(n_super < ctas ? n_super : ctas), SP_THREADS, SP_SMEM, (cudaStream_t)stream>>>(
