@@ -8,8 +8,8 @@ Outputs (git-ignored, but they travel to the GPU box with the gpurun snapshot):
                               nvcc defaults (-fmad=true), only -std=c++17 and the gencode differ
                               from the reference's setup.py:10-17.
   oracle/_ref/coder_ref.so  - the reference host arithmetic coder (coder/*.cpp).
-  oracle/_ref/refpy/        - the reference's Python layer (PCONV_operator/, model_zoo_v2, pseudo_codec) as sourceless byte
-                              code (.pyc), compiled from where it lies: tests/test_gpu_reference_python.py runs the reference's
+  oracle/_ref/refpy/        - the reference's Python layer (PCONV_operator/, model_zoo_v2, pseudo_codec) as marshalled
+                              code objects (.pcb), compiled from where it lies: tests/test_gpu_reference_python.py runs the reference's
                               own PseudoEncoder / PseudoDecoder on the GPU box against (a) the unmodified PCONV_ref / coder_ref
                               extensions - the real reference end to end - and (b) this repository's `PCONV` / `coder` mirrors
                               (INTEGRATION.md route A).
@@ -40,15 +40,22 @@ PY_MODULES = ["model_zoo_v2.py", "pseudo_codec.py"]
 
 
 def build_refpy():
-    """byte-compile the reference's Python layer into oracle/_ref/refpy (no source is copied)"""
-    import py_compile
+    """compile the reference's Python layer into oracle/_ref/refpy as marshalled code objects (`.pcb`; no source is copied, and
+    unlike `.pyc` the files are not filtered out of the snapshot that travels to the GPU box).  tests/ref_runner.py imports them
+    through a small meta-path finder."""
+    import marshal
     dst = os.path.join(OUT, "refpy")
     os.makedirs(os.path.join(dst, "PCONV_operator"), exist_ok=True)
-    pairs = [(os.path.join(REF, m), os.path.join(dst, m + "c")) for m in PY_MODULES]
+    pairs = [(os.path.join(REF, m), os.path.join(dst, m[:-3] + ".pcb")) for m in PY_MODULES]
     opdir = os.path.join(REF, "PCONV_operator")
-    pairs += [(os.path.join(opdir, f), os.path.join(dst, "PCONV_operator", f + "c")) for f in sorted(os.listdir(opdir)) if f.endswith(".py")]
+    pairs += [(os.path.join(opdir, f), os.path.join(dst, "PCONV_operator", f[:-3] + ".pcb")) for f in sorted(os.listdir(opdir)) if f.endswith(".py")]
     for src, out in pairs:
-        py_compile.compile(src, cfile=out, dfile=os.path.relpath(src, REF), doraise=True)
+        with open(src, "r", encoding="utf-8", errors="replace") as f:
+            code = compile(f.read(), os.path.relpath(src, REF), "exec", dont_inherit=True)
+        with open(out, "wb") as f:
+            f.write(marshal.dumps(code))
+    with open(os.path.join(dst, "PYTHON_VERSION"), "w") as f:
+        f.write("%d.%d" % sys.version_info[:2])
     print(f"[build_ref] {dst} ({len(pairs)} modules)")
 
 

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Runs the REFERENCE's own Python layer (pseudo_codec.PseudoEncoder / PseudoDecoder, byte code staged by oracle/build_ref.py
+"""Runs the REFERENCE's own Python layer (pseudo_codec.PseudoEncoder / PseudoDecoder, code objects staged by oracle/build_ref.py
 in oracle/_ref/refpy - no reference source lives in this repository) in a fresh interpreter, over one of two native back ends:
 
     --backend ref     the unmodified reference extensions compiled for sm_100 (oracle/_ref/PCONV_ref.so, coder_ref.so):
@@ -27,6 +27,41 @@ def _load_so(name):
     return mod
 
 
+class _BlobFinder:
+    """meta-path finder for the marshalled code objects of oracle/_ref/refpy (`name.pcb`, packages as `name/__init__.pcb`)"""
+
+    def __init__(self, base):
+        self.base = base
+
+    def _path(self, fullname):
+        rel = fullname.replace(".", os.sep)
+        pkg = os.path.join(self.base, rel, "__init__.pcb")
+        if os.path.exists(pkg):
+            return pkg, True
+        mod = os.path.join(self.base, rel + ".pcb")
+        return (mod, False) if os.path.exists(mod) else (None, False)
+
+    def find_spec(self, fullname, path=None, target=None):
+        import importlib.machinery
+        p, is_pkg = self._path(fullname)
+        if p is None:
+            return None
+        spec = importlib.machinery.ModuleSpec(fullname, self, origin=p, is_package=is_pkg)
+        if is_pkg:
+            spec.submodule_search_locations = [os.path.dirname(p)]
+        return spec
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        import marshal
+        with open(module.__spec__.origin, "rb") as f:
+            code = marshal.loads(f.read())
+        module.__file__ = module.__spec__.origin
+        exec(code, module.__dict__)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--backend", choices=["ref", "mirror"], required=True)
@@ -49,9 +84,9 @@ def main():
     fb = types.ModuleType("numpy.lib.function_base")
     fb.average, fb.interp = np.average, np.interp
     sys.modules["numpy.lib.function_base"] = fb
-    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref", "refpy"))
-    import pseudo_codec as ref_pc                      # the reference's module (sourceless byte code)
-    assert ref_pc.__file__.endswith(".pyc"), ref_pc.__file__
+    sys.meta_path.insert(0, _BlobFinder(os.path.join(ROOT, "oracle", "_ref", "refpy")))
+    import pseudo_codec as ref_pc                      # the reference's module (marshalled code object, no source here)
+    assert ref_pc.__file__.endswith(".pcb"), ref_pc.__file__
     torch.backends.cudnn.benchmark = False
     torch.backends.cudnn.deterministic = True
     torch.cuda.set_device(0)

@@ -81,27 +81,6 @@ def test_synthesis_transform_vs_cpu_port(both, cuda):
     assert np.abs(other - tc).max() > 1e-3
 
 
-def test_cpu_port_decodes_the_products_bitstream_symbols(both, cuda, tmp_path):
-    """Wire format across implementations: the product's bitstream, decoded by the port's wavefront loop + the reference-style
-    coder.  The port's GMM uses libm (CDF +-1 count of the GPU's), so a stream may derail where a symbol's code
-    value falls on a moved boundary; the check is therefore on the PREFIX that decodes - it has to be long."""
-    import torch
-    enc, dec, cpu, _ = both
-    x = torch.from_numpy(smooth_images(1, 3, 256, 512, seed=8)).to(cuda)
-    path = str(tmp_path / "p.bin")
-    sym = enc.symbols(x)
-    enc.ent.start(path)
-    enc.ent(sym.clone())
-    want = enc.ent.fill(sym.clone()).cpu().numpy()
-    try:
-        got = cpu.entropy_decode(path, 2, 64)
-    except Exception:
-        pytest.skip("the port's libm CDFs moved a boundary onto a code value: stream derailed (allowed, SURVEY.md H2)")
-    agree = float((got == want).mean())
-    assert agree > 0.5, agree
-    print("port decoded %.1f%% of the product's symbols identically" % (100 * agree))
-
-
 @pytest.mark.parametrize("Hs,Ws", [(1024, 2048), (2048, 4096)])
 def test_large_image_round_trip(both, cuda, tmp_path, Hs, Ws):
     """Sizes beyond the reference's hard-wired 512x1024 (pseudo_codec.py:206-209): one-shot encoder with automatic slabs,
