@@ -331,12 +331,19 @@ def load_models(model: nn.Module, p1, p2, device):
     model.load_state_dict(OrderedDict(**d2, **d1))
 
 
-def check_img(img):
+def check_img(img, height=512, width=1024):
+    """The reference resizes every input to 1024 x 512 (pseudo_codec.py:229-234); --height / --width generalise that (f3):
+    the coded size must be a multiple of 256 x 128 (16 bands x 16-fold down-sampling; 8 code columns per context cell)."""
     import cv2
     h, w = img.shape[:2]
-    if not (h == 512 and w == 1024):
-        return cv2.resize(img, (1024, 512), interpolation=cv2.INTER_CUBIC)
+    if not (h == height and w == width):
+        return cv2.resize(img, (width, height), interpolation=cv2.INTER_CUBIC)
     return img
+
+
+def _check_size(height, width):
+    assert height % 256 == 0 and width % 128 == 0 and height > 0 and width > 0, \
+        'image size must be a multiple of 256 rows x 128 columns (got {}x{})'.format(height, width)
 
 
 def _select(model_idx, mse):
@@ -345,36 +352,39 @@ def _select(model_idx, mse):
     return prex, vd, (mse_model_dir if mse else ssim_model_dir)
 
 
-def encoding(img_list, out_list, model_idx=0, mse=True, device_id=0):
+def encoding(img_list, out_list, model_idx=0, mse=True, device_id=0, height=512, width=1024):
     import cv2
+    _check_size(height, width)
     prex, vd, model_dir = _select(model_idx, mse)
     cuda = 'cuda:{}'.format(device_id)
     t1 = PseudoEncoder(vd, device_id=device_id).to(cuda)
     load_models(t1, '{}/{}_encoder.pt'.format(model_dir, prex), '{}/{}_ent.pt'.format(model_dir, prex), cuda)
     for fn, fo in zip(img_list, out_list):
-        data = img2tensor(check_img(cv2.imread(fn)), cuda)
+        data = img2tensor(check_img(cv2.imread(fn), height, width), cuda)
         t1(data, fo)
-        print('Encoding {}, bitrate: {:.3f}bpp'.format(fn, os.path.getsize(fo) * 8 / 1024. / 512.))
+        print('Encoding {}, bitrate: {:.3f}bpp'.format(fn, os.path.getsize(fo) * 8 / float(width) / float(height)))
 
 
-def decoding(code_list, decoded_img_list, model_idx=0, mse=True, device_id=0):
+def decoding(code_list, decoded_img_list, model_idx=0, mse=True, device_id=0, height=512, width=1024):
     import cv2
+    _check_size(height, width)
     prex, vd, model_dir = _select(model_idx, mse)
     cuda = 'cuda:{}'.format(device_id)
     t1 = PseudoDecoder(vd, device_id=device_id).to(cuda)
     load_models(t1, '{}/{}_decoder.pt'.format(model_dir, prex), '{}/{}_ent.pt'.format(model_dir, prex), cuda)
     for fc, fo in zip(code_list, decoded_img_list):
-        cv2.imwrite(fo, tensor2img(t1(fc)))
+        cv2.imwrite(fo, tensor2img(t1(fc, height, width)))
         print('Decoding {}, output to {}'.format(fc, fo))
 
 
-def decoding_and_test(code_list, img_list, model_idx=0, mse=True, device_id=0):
+def decoding_and_test(code_list, img_list, model_idx=0, mse=True, device_id=0, height=512, width=1024):
     """Decode and report bitrate, viewport PSNR and viewport SSIM like the reference (pseudo_codec.py:262-290): source and
     reconstruction are sampled on 14 rectilinear viewports of 171 x 256 pixels (MultiProject, fov 0.5 pi), PSNR from the
     mean squared difference, SSIM with an 11-tap Gaussian window."""
     import cv2
     from .PCONV_operator import MultiProject, SSIM
     from .PCONV_operator.pytorch_ssim import mean_squared_difference
+    _check_size(height, width)
     prex, vd, model_dir = _select(model_idx, mse)
     cuda = 'cuda:{}'.format(device_id)
     t1 = PseudoDecoder(vd, device_id=device_id).to(cuda)
@@ -384,13 +394,13 @@ def decoding_and_test(code_list, img_list, model_idx=0, mse=True, device_id=0):
     sim_func = SSIM(11, 3).to(cuda)
     rt_list, pr_list, ssim_list = [], [], []
     for fc, fn in zip(code_list, img_list):
-        rdata = t1(fc)
-        data = img2tensor(check_img(cv2.imread(fn)), cuda)
+        rdata = t1(fc, height, width)
+        data = img2tensor(check_img(cv2.imread(fn), height, width), cuda)
         x = pr1(data)
         y = pr2(rdata)
         pr = psnr_f(mean_squared_difference(x, y).item())
         vssim = sim_func(x, y).item()
-        rt = os.path.getsize(fc) * 8 / 1024. / 512.
+        rt = os.path.getsize(fc) * 8 / float(width) / float(height)
         rt_list.append(rt)
         pr_list.append(pr)
         ssim_list.append(vssim)
@@ -428,6 +438,9 @@ def main(argv=None):
     parser.add_argument('--ssim', action='store_true', default=False, help='Default with models optimized for VMSE, '
                         'set this flag for choosing the models optimized for VSSIM')
     parser.add_argument('--gpu-id', type=int, default=0, help='The graphic card id for encoding and decoding.')
+    parser.add_argument('--height', type=int, default=512, help='Coded image height (multiple of 256); inputs are resized to it. '
+                        'The bitstream has no header: pass the same size when decoding. Default 512 like the reference.')
+    parser.add_argument('--width', type=int, default=1024, help='Coded image width (multiple of 128). Default 1024 like the reference.')
     args = parser.parse_args(argv)
     check_models()
     midx = args.model_idx
@@ -442,17 +455,17 @@ def main(argv=None):
         assert img_list is not None, 'No input images for encoding'
         assert code_list is not None, 'No code files for saving the codes'
         assert len(img_list) == len(code_list), 'The number of images and codes should be the same'
-        encoding(img_list, code_list, midx, not args.ssim, args.gpu_id)
+        encoding(img_list, code_list, midx, not args.ssim, args.gpu_id, args.height, args.width)
     else:
         assert code_list is not None, 'No code files for decoding'
         if args.dec:
             assert out_list is not None, 'No out files for saving the decoded images'
             assert len(code_list) == len(out_list), 'The number of codes and reconstructed images should be the same'
-            decoding(code_list, out_list, midx, not args.ssim, args.gpu_id)
+            decoding(code_list, out_list, midx, not args.ssim, args.gpu_id, args.height, args.width)
         else:
             assert img_list is not None, 'No source images for evaluation.'
             assert len(code_list) == len(img_list), 'The number of codes and corresponding source images should be the same'
-            decoding_and_test(code_list, img_list, midx, not args.ssim, args.gpu_id)
+            decoding_and_test(code_list, img_list, midx, not args.ssim, args.gpu_id, args.height, args.width)
 
 
 if __name__ == '__main__':

@@ -104,3 +104,30 @@ def test_command_line_enc_dec_test(cuda, tmp_path, monkeypatch, capsys):
     ssim = float(last.split("SSIM:")[1])
     assert abs(rate - np.mean([os.path.getsize(c) * 8 / 1024. / 512. for c in codes])) < 1e-3
     assert 3.0 < psnr < 60.0 and -1.0 <= ssim <= 1.0                     # random-init weights: only sanity, not quality
+
+
+def test_command_line_other_sizes(cuda, tmp_path, monkeypatch, capsys):
+    """--height / --width: the reference resizes everything to 1024 x 512 and hard-wires the code size
+    (pseudo_codec.py:206-209, :229-234); here the coded size is an option on all three commands, default unchanged.  Inputs of
+    another size are resized to it, the bitrate is reported per coded pixel, a bad size is refused."""
+    import cv2
+    from pseudocylindrical_convolution_b200 import pseudo_codec as pc
+    from pseudocylindrical_convolution_b200.random_init import synthesize_checkpoints
+    monkeypatch.chdir(tmp_path)
+    for d, p in (("./demo/ssim", "4_56"), ("./demo/ssim", "1_56"), ("./demo/mse", "1_56")):
+        synthesize_checkpoints(d, p, 56, 0, seed=0)
+    arr = (smooth_images(1, 3, 300, 700, seed=9)[0].transpose(1, 2, 0) * 255).astype(np.uint8)      # not the coded size: resized
+    img, code, out = str(tmp_path / "a.png"), str(tmp_path / "a.bin"), str(tmp_path / "a_rec.png")
+    cv2.imwrite(img, arr)
+    size = ["--height", "256", "--width", "768"]
+    pc.main(["--enc", "--ssim", "--model-idx", "3", "--img-list", img, "--code-list", code] + size)
+    text = capsys.readouterr().out
+    rate = float(text.split("bitrate:")[1].split("bpp")[0])
+    assert abs(rate - os.path.getsize(code) * 8 / (256 * 768)) < 1e-3
+    pc.main(["--dec", "--ssim", "--model-idx", "3", "--code-list", code, "--out-list", out] + size)
+    rec = cv2.imread(out)
+    assert rec is not None and rec.shape == (256, 768, 3)
+    pc.main(["--test", "--ssim", "--model-idx", "3", "--code-list", code, "--img-list", img] + size)
+    assert "Average Performance" in capsys.readouterr().out
+    with pytest.raises(AssertionError):
+        pc.main(["--enc", "--ssim", "--model-idx", "3", "--img-list", img, "--code-list", code, "--height", "300", "--width", "768"])
