@@ -44,12 +44,60 @@ struct FlowNet {
     unsigned *host_ctl;           // mapped host memory: [0] host -> device abort request, [1] device -> host error word
     unsigned *dev_ctl;            // device memory: [0] abort flag, [16 + img] = steps whose input symbols are in place
     unsigned long long timeout_ns;
+    const float *packed;          // weight images (flow_pack_weights_kernel), wbuf floats per (layer, net, channel group)
     unsigned long long *trace;    // optional (PCX_WAVE_TRACE): per step 4 globaltimer stamps of image 0's leader block
 };
 
 __global__ void fill_u32_kernel(unsigned *p, size_t n, unsigned v)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// Weight rows in the layout the step kernels keep in shared memory, once per decode: packed[((L * nb + b) * G + tc)] is the
+// image of outputs tc*3 .. tc*3+2 of net b in layer L - [ci * 25 + tap][og] floats (4 per entry, the three outputs + padding),
+// then bias and slope at 4 * wstride.  Staging a (layer, net, channel group) for a run is then a straight 16-byte cp.async
+// copy; the gather form (step_stage_weights: 4-byte copies, two integer divisions each) cost every thread ~400 instructions
+// per run, as much as the run's arithmetic when a block's runs are 8 cells long (batches).
+__global__ void flow_pack_weights_kernel(const StepNet d, float *__restrict__ packed, int wbuf)
+{
+    const int G = d.G, Co = G * 3;
+    const i64 per_layer = (i64)d.nb * G * wbuf;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < per_layer * d.nlayers; i += (i64)gridDim.x * blockDim.x) {
+        const int L = (int)(i / per_layer);
+        const i64 r0 = i - L * per_layer;
+        const int bt = (int)(r0 / wbuf), e = (int)(r0 - (i64)bt * wbuf);
+        const int b = bt / G, tc = bt - b * G;
+        const StepLayer &l = d.L[L];
+        const int Ci = G * l.gi, nw = Ci * 25, tail = 4 * G * 3 * 25;
+        float v = 0.f;
+        if (e < 4 * nw) {
+            const int r = e >> 2, og = e & 3;
+            if (og < 3) v = l.weight[(((i64)b * Co + tc * 3 + og) * Ci) * 25 + r];
+        } else if (e >= tail && e < tail + 3) {
+            v = l.bias[b * Co + tc * 3 + (e - tail)];
+        } else if (e >= tail + 3 && e < tail + 6 && l.act != nullptr) {
+            v = l.act[b * Co + tc * 3 + (e - tail - 3)];
+        }
+        packed[i] = v;
+    }
+}
+
+__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// the first gmax channel groups of the packed image (+ bias / slope) into a shared-memory weight buffer
+__device__ __forceinline__ void flow_stage_packed(const StepNet &d, const float *packed, int wbuf, int L, int b, int tc, float *smem)
+{
+    const StepLayer &l = d.L[L];
+    int gmax = tc + 4 + (l.constrain == 6 ? 1 : 0);
+    gmax = gmax > d.G ? d.G : gmax;
+    const int nvec = gmax * l.gi * 25;                                    // 16-byte entries
+    const float *src = packed + (((i64)L * d.nb + b) * d.G + tc) * wbuf;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) cp_async16(smem + 4 * i, src + 4 * i);
+    const int tail = 4 * d.G * 3 * 25;
+    if (threadIdx.x < 2) cp_async16(smem + tail + 4 * threadIdx.x, src + tail + 4 * threadIdx.x);
 }
 
 __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p)
@@ -98,6 +146,7 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_flow_kernel(const __grid_co
     const int tid = threadIdx.x;
     const int h = d.h, W = d.W, pad = d.pad, G = d.G;
     const int wstride = G * 3 * 25;
+    const int wbuf = 4 * wstride + 8;                 // floats per weight buffer / packed image
     const int *__restrict__ start = f.start;
     FlowCtl ctl;
     ctl.abort_flag = f.dev_ctl;
@@ -124,10 +173,14 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_flow_kernel(const __grid_co
             first = start[p0];
             count = start[p0 + np] - first;
         }
-        const int nmy = bi < nchunk ? (nchunk - 1 - bi) / B + 1 : 0;      // my runs per layer
+        // the block's runs: a CONTIGUOUS range of the step's run list (ordered plane, net, run) - consecutive runs mostly share
+        // their (net, plane), i.e. their weight rows, which are then staged once
+        const int per = (nchunk + B - 1) / B;
+        const int c_first = bi * per;
+        const int nmy = c_first < nchunk ? (nchunk - c_first < per ? nchunk - c_first : per) : 0;
         const int nitems = nmy * d.nlayers;
         if (tracer) f.trace[(size_t)step * 16 + 0] = flow_now();
-        if (tid < nmy && tid < STEP_MAX_RUNS) s_chunk[tid] = step_chunk_of(start, bi + tid * B, p0, np, S, d.nb, 1);
+        if (tid < nmy && tid < STEP_MAX_RUNS) s_chunk[tid] = step_chunk_of(start, c_first + tid, p0, np, S, d.nb, 1);
         __syncthreads();
         if (tid == 0) {
             int acc = 0;
@@ -156,7 +209,7 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_flow_kernel(const __grid_co
         }
         if (nitems > 0) {
             const StepChunk c0 = s_chunk[0];
-            step_stage_weights(d, d.L[0], c0.net, step - c0.plane, step_ws, wstride);
+            flow_stage_packed(d, f.packed, wbuf, 0, c0.net, step - c0.plane, step_ws);
         }
         cp_async_commit();
 
@@ -225,23 +278,26 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_flow_kernel(const __grid_co
         if (tracer) f.trace[(size_t)step * 16 + 1] = flow_now();
 
         // ---- the masked layers: no barrier between them, consumers poll the scalars they need (step_conv_phase<GI, true>)
-        int it = 0;
+        int it = 0, buf = 0;
         for (int L = 0; L < d.nlayers; L++) {
             for (int ci = 0; ci < nmy; ci++, it++) {
-                const StepChunk ch = ci < STEP_MAX_RUNS ? s_chunk[ci] : step_chunk_of(start, bi + ci * B, p0, np, S, d.nb, 1);
-                if (it > 0) __syncthreads();           // every warp is done with item it-1: its weight buffer may be refilled
+                const StepChunk ch = ci < STEP_MAX_RUNS ? s_chunk[ci] : step_chunk_of(start, c_first + ci, p0, np, S, d.nb, 1);
+                if (it > 0) __syncthreads();           // every warp is done with item it-1: the other weight buffer may be refilled
+                bool restage = false;
                 if (it + 1 < nitems) {
                     const int nci = ci + 1 < nmy ? ci + 1 : 0, nL = ci + 1 < nmy ? L : L + 1;
-                    const StepChunk nc = nci < STEP_MAX_RUNS ? s_chunk[nci] : step_chunk_of(start, bi + nci * B, p0, np, S, d.nb, 1);
-                    step_stage_weights(d, d.L[nL], nc.net, step - nc.plane, step_ws + ((it + 1) & 1) * (4 * wstride + 8), wstride);
+                    const StepChunk nc = nci < STEP_MAX_RUNS ? s_chunk[nci] : step_chunk_of(start, c_first + nci, p0, np, S, d.nb, 1);
+                    restage = nL != L || nc.net != ch.net || nc.plane != ch.plane;       // same rows: the next run reuses this buffer
+                    if (restage) flow_stage_packed(d, f.packed, wbuf, nL, nc.net, step - nc.plane, step_ws + (buf ^ 1) * wbuf);
                 }
                 cp_async_commit();
                 cp_async_wait<1>();                    // this item's rows have landed; the next item's may still be in flight
                 __syncthreads();
-                const float *ws = step_ws + (it & 1) * (4 * wstride + 8);
+                const float *ws = step_ws + buf * wbuf;
                 const int cbase = ci < STEP_MAX_RUNS ? s_cache_base[ci] : STEP_CACHE_CELLS;
                 if (d.L[L].gi == 1) step_conv_phase<1, true>(d, d.L[L], step, ch, start, ws, wstride, s_tap, s_cell, cbase, img, &ctl);
                 else step_conv_phase<3, true>(d, d.L[L], step, ch, start, ws, wstride, s_tap, s_cell, cbase, img, &ctl);
+                if (restage) buf ^= 1;
             }
             if (tracer && L < 12) f.trace[(size_t)step * 16 + 2 + L] = flow_now();
         }
@@ -289,6 +345,8 @@ struct FlowState {                  // per device, created on first use, guarded
     int *d_start = nullptr;
     int4 *d_sched = nullptr;
     size_t start_cap = 0, sched_cap = 0;
+    float *d_packed = nullptr;      // weight images
+    size_t packed_cap = 0;
     uint4 *h_rows = nullptr;        // mapped
     unsigned *h_symw = nullptr;     // mapped
     unsigned *h_ctl = nullptr;      // mapped
@@ -460,6 +518,14 @@ int pcx_wave_decode_flow(const pcx_wave_net &n, pcx_coder *const *coders, long l
         PCX_LAUNCHED();
     }
     PCX_CUDA(cudaMemsetAsync(st.dev_ctl, 0, sizeof(unsigned) * (16 + 1024), s));
+    const int wbuf = 4 * n.G * 3 * 25 + 8;
+    const size_t packed_floats = (size_t)n.nlayers * n.nb * n.G * wbuf;
+    if (packed_floats > st.packed_cap) {
+        if (st.d_packed) cudaFree(st.d_packed);
+        st.d_packed = nullptr; st.packed_cap = 0;
+        PCX_CUDA(cudaMalloc((void **)&st.d_packed, sizeof(float) * packed_floats));
+        st.packed_cap = packed_floats;
+    }
     PCX_CUDA(cudaMemcpyAsync(st.d_start, n.h_start, sizeof(int) * (size_t)(nplanes + 1), cudaMemcpyHostToDevice, s));
     PCX_CUDA(cudaMemcpyAsync(st.d_sched, sched.data(), sizeof(int4) * (size_t)nsteps, cudaMemcpyHostToDevice, s));
     for (int L = 0; L < n.nlayers; L++) {
@@ -491,6 +557,9 @@ int pcx_wave_decode_flow(const pcx_wave_net &n, pcx_coder *const *coders, long l
         d.halo_one = fo;
     }
     PCX_CUDA(cudaMemsetAsync(n.layers[0].in, 0, sizeof(float) * (size_t)nrep * n.npart * n.G * (n.h + 2 * n.pad) * (n.W + 2 * n.pad), s));
+    flow_pack_weights_kernel<<<pcx_sm_count() * 4, 256, 0, s>>>(d, st.d_packed, wbuf);      // after d.L[] is filled in above
+    PCX_LAUNCHED();
+    f.packed = st.d_packed;
     f.nsteps = nsteps; f.rows_cap = rows_cap; f.blocks_per_img = B;
     const unsigned salt = (st.epoch++ * 9973u) & 0x7fffu;
     f.tag_salt = salt;
