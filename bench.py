@@ -308,6 +308,11 @@ def time_tile_pipeline(dev, local, rank, peaks, sharding, steps=2, warmup=1, nim
     flops = 2.0 * 9 * CI * CO * valid
     tf32_peak = peaks["bf16_sustained"] / 2.0
     tfl = flops / (k_ms["conv"] / 1e3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("conv_dram_bytes_per_launch")
     b_sp = 4.0 * (CI * Ht * Wt + CI * sum((h + 2) * (w + 2) for w in wl))
     b_us = 4.0 * (CO * valid + CO * Ht * Wt)
     hbm = [{"kernel": "slice_pad_v3_kernel (SphereSlice + PseudoPadV2 + layout change)", "bound": "hbm", "achieved": b_sp / (k_ms["slice_pad"] / 1e3) / 1e9,
@@ -319,7 +324,11 @@ def time_tile_pipeline(dev, local, rank, peaks, sharding, steps=2, warmup=1, nim
     res = {"workload": "configs[1] tile pipeline: slice->pad(1)->pconv3x3(192->192)->fill->uslice, %d x 192x1024x2048 fp32 per GPU, device-resident" % nimg,
            "value": value, "unit": UNIT, "ms_per_step": sec * 1e3, "steps": steps,
            "conv": {"kernel": "conv_pair_kernel<192> (tcgen05 cta_group::2 kind::tf32)", "bound": "tensor", "achieved": tfl, "peak": tf32_peak,
-                    "unit": "TFLOP/s", "frac": tfl / tf32_peak, "avg_launch_ms": k_ms["conv"], "flops_per_launch": flops}}
+                    "unit": "TFLOP/s", "frac": tfl / tf32_peak, "avg_launch_ms": k_ms["conv"], "flops_per_launch": flops,
+                    "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full capture of this kernel, per launch)",
+                    "alt_denominators": {"cublas_tf32_8192_burst_TFLOPs": 734.0, "cublas_tf32_8192_sustained_TFLOPs": 620.0,
+                                         "tcgen05_tf32_issue_limit_TFLOPs_at_1.9GHz": 1035.0,
+                                         "source": "profiles/r1_tf32_matmul_peak.json, profiles/r1_umma_peak2.txt (tools/tf32_matmul_peak.py, tools/umma_peak.cu)"}}}
     del x, out, pipe
     torch.cuda.empty_cache()
     return res, hbm

@@ -579,13 +579,21 @@ int pcx_wave_decode_flow(const pcx_wave_net &n, pcx_coder *const *coders, long l
         }
     }
 
+    // The launch goes through a helper thread: the kernel needs this thread's decoder loop below to make progress, and a
+    // launch call that only returns when the kernel has finished (a profiler that serialises launches, e.g. the ncu launch-list
+    // pass) would otherwise dead-lock against it until the device time-out.  Normally the call returns at once.
     void *args[] = {(void *)&f};
-    cudaError_t le = cudaLaunchCooperativeKernel((const void *)wave_flow_kernel, dim3(B * n.nimg), dim3(threads), args, smem, s);
-    if (le != cudaSuccess) {
-        if (h_trace) cudaFreeHost(h_trace);
-        pcx_set_error("%s:%d cooperative launch of the decoder kernel -> %s", __FILE__, __LINE__, cudaGetErrorString(le));
-        return PCX_ECUDA;
-    }
+    int launch_dev = 0;
+    PCX_CUDA(cudaGetDevice(&launch_dev));
+    std::atomic<int> launch_state{0};                  // 0 pending, 1 returned ok, -1 failed
+    cudaError_t le = cudaSuccess;
+    const int grid = B * n.nimg;
+    std::thread launcher([&] {
+        cudaError_t e = cudaSetDevice(launch_dev);
+        if (e == cudaSuccess) e = cudaLaunchCooperativeKernel((const void *)wave_flow_kernel, dim3(grid), dim3(threads), args, smem, s);
+        le = e;
+        launch_state.store(e == cudaSuccess ? 1 : -1, std::memory_order_release);
+    });
     g_pcx_launches.fetch_add(1, std::memory_order_relaxed);
 
     // ---- host decoders: T threads, thread t serves images t, t + T, ...; each image is its own state machine
@@ -655,6 +663,7 @@ int pcx_wave_decode_flow(const pcx_wave_net &n, pcx_coder *const *coders, long l
             _mm_pause();
             if ((++idle & 1023u) == 0) {
                 if (h_ctl[1] != 0) { status.store(PCX_ECUDA); break; }                 // the device gave up (time-out)
+                if (launch_state.load(std::memory_order_acquire) < 0) { status.store(PCX_ECUDA); break; }      // the kernel never started
                 const auto now = std::chrono::steady_clock::now();
                 if (idle == 1024u) last_progress = now;
                 else if (std::chrono::duration<double>(now - last_progress).count() > 30.0) { status.store(PCX_ECUDA); break; }
@@ -667,6 +676,14 @@ int pcx_wave_decode_flow(const pcx_wave_net &n, pcx_coder *const *coders, long l
     for (int t = 1; t < T; t++) workers.emplace_back(serve, t);
     serve(0);
     for (auto &w : workers) w.join();
+    if (status.load() != PCX_OK) h_ctl[0] = 1;         // tell the kernel to stop waiting (before joining a launch call that may block on it)
+    launcher.join();
+    if (le != cudaSuccess) {
+        if (h_trace) cudaFreeHost(h_trace);
+        if (dump) fclose(dump);
+        pcx_set_error("%s:%d cooperative launch of the decoder kernel -> %s", __FILE__, __LINE__, cudaGetErrorString(le));
+        return PCX_ECUDA;
+    }
     if (dump) {
         for (size_t q = 0; q < log_rows.size(); q++) {
             const uint16_t *row = reinterpret_cast<const uint16_t *>(&log_rows[q]);
