@@ -408,6 +408,78 @@ __device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLaye
         float acc[GI][3];
 #pragma unroll
         for (int m = 0; m < GI; m++) acc[m][0] = acc[m][1] = acc[m][2] = 0.f;
+        if (FLOW) {
+            // The chain's LAST element (the only one that can belong to the current step) is fetched on its own, straight from
+            // L2, together with the batches of the earlier elements - all loads of the task's first round trip in flight at once.
+            // (The first version validated the loaded batches in place: ~150 compare / select instructions per batch to find one
+            // run-time-indexed element in registers - 45 % of a task's cycles at the ~10 cycles per instruction of this
+            // latency-bound kernel, measured with clock64.)  The prefix k < nk - 1 runs through the batched loop, the last FFMA
+            // of every chain follows it: same ascending order.
+            float la[GI], lb[GI];
+#pragma unroll
+            for (int m = 0; m < GI; m++) la[m] = lb[m] = 0.f;
+            const bool use_a = nk > 0 && tp.mode != 2, use_b = nk > 0 && (tp.mode == 1 || tp.mode == 2);
+            if (use_a) {
+#pragma unroll
+                for (int m = 0; m < GI; m++) la[m] = flow_ld(tp.pa + (nk - 1) * GI + m);
+            }
+            if (use_b) {
+#pragma unroll
+                for (int m = 0; m < GI; m++) lb[m] = flow_ld(tp.pb + (nk - 1) * GI + m);
+            }
+            const int np = nk - 1;                                // elements of the batched prefix
+            for (int c0 = 0; c0 < gmax - 1; c0 += 8) {
+                const int on = np > c0;
+                float4 xa[NQ], xb[NQ];
+#pragma unroll
+                for (int q = 0; q < NQ; q++) xa[q] = xb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                ld_ca_batch<NQ>(xa, tp.pa + c0 * GI, on && tp.mode != 2);
+                ld_ca_batch<NQ>(xb, tp.pb + c0 * GI, on && (tp.mode == 1 || tp.mode == 2));
+                float va[8 * GI];
+#pragma unroll
+                for (int q = 0; q < NQ; q++) { va[4 * q] = xa[q].x; va[4 * q + 1] = xa[q].y; va[4 * q + 2] = xa[q].z; va[4 * q + 3] = xa[q].w; }
+                if (tp.mode != 0) {                              // halo / wrap-of-halo tap: causal 2-tap interpolation (+0 when mode 2 / 4)
+                    float vb[8 * GI];
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) { vb[4 * q] = xb[q].x; vb[4 * q + 1] = xb[q].y; vb[4 * q + 2] = xb[q].z; vb[4 * q + 3] = xb[q].w; }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        if (c0 + u < np) {
+#pragma unroll
+                            for (int m = 0; m < GI; m++) va[u * GI + m] = lerp2_ref(va[u * GI + m], vb[u * GI + m], tp.t);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (c0 + u < np) {
+#pragma unroll
+                        for (int m = 0; m < GI; m++) {
+                            const float4 w = wl_[((c0 + u) * GI + m) * 25];
+                            const float v = va[u * GI + m];
+                            acc[m][0] = __fmaf_rn(v, w.x, acc[m][0]);
+                            acc[m][1] = __fmaf_rn(v, w.y, acc[m][1]);
+                            acc[m][2] = __fmaf_rn(v, w.z, acc[m][2]);
+                        }
+                    }
+                }
+            }
+            if (nk > 0) {
+#pragma unroll
+                for (int m = 0; m < GI; m++) {
+                    if (use_a && __float_as_uint(la[m]) == FLOW_SENTINEL) la[m] = flow_poll(tp.pa + np * GI + m, ctl);
+                    if (use_b && __float_as_uint(lb[m]) == FLOW_SENTINEL) lb[m] = flow_poll(tp.pb + np * GI + m, ctl);
+                }
+#pragma unroll
+                for (int m = 0; m < GI; m++) {
+                    const float v = tp.mode == 0 ? la[m] : lerp2_ref(la[m], lb[m], tp.t);
+                    const float4 w = wl_[(np * GI + m) * 25];
+                    acc[m][0] = __fmaf_rn(v, w.x, acc[m][0]);
+                    acc[m][1] = __fmaf_rn(v, w.y, acc[m][1]);
+                    acc[m][2] = __fmaf_rn(v, w.z, acc[m][2]);
+                }
+            }
+        } else
         for (int c0 = 0; c0 < gmax; c0 += 8) {
             const int on = nk > c0;
             float4 xa[NQ], xb[NQ];
@@ -419,13 +491,10 @@ __device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLaye
             float va[8 * GI];
 #pragma unroll
             for (int q = 0; q < NQ; q++) { va[4 * q] = xa[q].x; va[4 * q + 1] = xa[q].y; va[4 * q + 2] = xa[q].z; va[4 * q + 3] = xa[q].w; }
-            if (FLOW && on && nk <= c0 + 8 && tp.mode != 2)     // the chain ends in this batch: its last element may be of this step
-                flow_validate<GI>(va, nk - 1 - c0, tp.pa + (nk - 1) * GI, ctl);
             if (tp.mode != 0) {                                  // halo / wrap-of-halo tap: causal 2-tap interpolation (+0 when mode 2)
                 float vb[8 * GI];
 #pragma unroll
                 for (int q = 0; q < NQ; q++) { vb[4 * q] = xb[q].x; vb[4 * q + 1] = xb[q].y; vb[4 * q + 2] = xb[q].z; vb[4 * q + 3] = xb[q].w; }
-                if (FLOW && on && nk <= c0 + 8 && tp.mode != 4) flow_validate<GI>(vb, nk - 1 - c0, tp.pb + (nk - 1) * GI, ctl);
 #pragma unroll
                 for (int e = 0; e < 8 * GI; e++) va[e] = lerp2_ref(va[e], vb[e], tp.t);
             }
