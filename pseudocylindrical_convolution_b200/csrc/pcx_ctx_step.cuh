@@ -383,6 +383,14 @@ __device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLaye
     gmax = gmax > G ? G : gmax;
     const float4 *wl_ = reinterpret_cast<const float4 *>(ws) + kh * 5 + kw;
     for (int k = warp; k < ch.ncell; k += nwarp) {
+#ifdef PCX_FLOW_PROBE
+        const bool probe = FLOW && d.dbg != nullptr && blockIdx.x == d.nimg && warp == 0;      // block 1 of image 0, warp 0
+        long long pt[6] = {0, 0, 0, 0, 0, 0};
+        if (probe) { __syncwarp(); pt[0] = clock64(); }
+#define PCX_PROBE(i) if (probe) { __syncwarp(); pt[i] = clock64(); }
+#else
+#define PCX_PROBE(i)
+#endif
         int pn, tw, g, th;
         StepTap tp;
         tp.pa = tp.pb = l.in;
@@ -428,6 +436,10 @@ __device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLaye
                 for (int m = 0; m < GI; m++) lb[m] = flow_ld(tp.pb + (nk - 1) * GI + m);
             }
             const int np = nk - 1;                                // elements of the batched prefix
+            PCX_PROBE(1)
+            // (A two-stage pipeline - the loads of batch i + 1 issued before batch i's FFMAs - cuts the prefix phase from 5000 to
+            // 4000 cycles per task in the clock64 probe below, but needs 199 registers: one block per SM, or 200 bytes of spills at
+            // 128 registers - 64.5 -> 106 / 85.7 ms for 8 images.  Dropped.)
             for (int c0 = 0; c0 < gmax - 1; c0 += 8) {
                 const int on = np > c0;
                 float4 xa[NQ], xb[NQ];
@@ -464,12 +476,16 @@ __device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLaye
                     }
                 }
             }
+            PCX_PROBE(2)
             if (nk > 0) {
 #pragma unroll
                 for (int m = 0; m < GI; m++) {
                     if (use_a && __float_as_uint(la[m]) == FLOW_SENTINEL) la[m] = flow_poll(tp.pa + np * GI + m, ctl);
                     if (use_b && __float_as_uint(lb[m]) == FLOW_SENTINEL) lb[m] = flow_poll(tp.pb + np * GI + m, ctl);
                 }
+            }
+            PCX_PROBE(3)
+            if (nk > 0) {
 #pragma unroll
                 for (int m = 0; m < GI; m++) {
                     const float v = tp.mode == 0 ? la[m] : lerp2_ref(la[m], lb[m], tp.t);
@@ -512,6 +528,7 @@ __device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLaye
                 }
             }
         }
+        PCX_PROBE(4)
         // chain (m, tap) = reference lane i = m*25 + tap; lane t now collects lanes t, t+32, t+64
         float sum[3];
 #pragma unroll
@@ -551,6 +568,20 @@ __device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLaye
                 else l.out[o + og] = v;
             }
         }
+#ifdef PCX_FLOW_PROBE
+        if (probe) {
+            __syncwarp();
+            const long long t = clock64();
+            if (lane == 0) {       // cycles: setup + issue | prefix (load latency + FMAs) | wait for the last elements | last FMAs | fold + store
+                atomicAdd(d.dbg + 0, (unsigned long long)(pt[1] - pt[0]));
+                atomicAdd(d.dbg + 1, (unsigned long long)(pt[2] - pt[1]));
+                atomicAdd(d.dbg + 2, (unsigned long long)(pt[3] ? pt[3] - pt[2] : 0));
+                atomicAdd(d.dbg + 3, (unsigned long long)(pt[4] - (pt[3] ? pt[3] : pt[2])));
+                atomicAdd(d.dbg + 4, (unsigned long long)(t - pt[4]));
+                atomicAdd(d.dbg + 5, 1ull);
+            }
+        }
+#endif
     }
 }
 

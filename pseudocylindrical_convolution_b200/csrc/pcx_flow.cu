@@ -871,8 +871,8 @@ int pcx_wave_decode_flow(const pcx_wave_net &n, pcx_coder *const *coders, long l
         unsigned long long hp[8] = {0};
         cudaMemcpy(hp, d_probe, 64, cudaMemcpyDeviceToHost);
         cudaFree(d_probe);
-        if (hp[4]) fprintf(stderr, "[flow probe] tasks %llu: cycles per task %.0f | waiting for loads %.0f | validate+lerp (polls) %.0f | start -> FMAs done %.0f\n",
-                           hp[4], (double)hp[0] / hp[4], (double)hp[1] / hp[4], (double)hp[2] / hp[4], (double)hp[3] / hp[4]);
+        if (hp[5]) fprintf(stderr, "[flow probe] %llu tasks, cycles per task: setup + issue %.0f | prefix (load latency + FMAs) %.0f | wait for last elements %.0f | last FMAs %.0f | fold + store %.0f\n",
+                           hp[5], (double)hp[0] / hp[5], (double)hp[1] / hp[5], (double)hp[2] / hp[5], (double)hp[3] / hp[5], (double)hp[4] / hp[5]);
     }
 #endif
     const unsigned dev_err = h_ctl[1];
