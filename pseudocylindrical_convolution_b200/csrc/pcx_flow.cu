@@ -138,159 +138,10 @@ __device__ __noinline__ unsigned flow_poll_symbol(const FlowNet &f, const unsign
     return w;
 }
 
-// ---------------------------------------------------------------------------------------------- C cells per warp (batches)
-// The warp-per-cell task is bound by the load / store pipe, not by arithmetic: every weight (one 128-bit shared load per
-// channel and tap) is used for ONE cell, ~190 of the ~400 LSU cycles of a task.  With several images per GPU a block's run has
-// plenty of cells, so a warp takes C consecutive cells of the run - same net, same plane, hence the same weight rows - and every
-// weight load feeds C FFMA triples.  Lane = tap as before; per cell the same chains in the same order and the same fold tree:
-// bit-identical results.  Scratch layout of this form: element (group k, member m) of a cell at m * G8 + k, so the 8 groups a
-// lane multiplies with one weight block are two 128-bit loads per cell and member.
-template <int GI, int C>
-__device__ __forceinline__ void flow_conv_multi(const StepNet &d, const StepLayer &l, int step, const StepChunk &ch, const int *start,
-                                                const float *ws, int wstride, const StepTapOff *tap_cache, const StepCellRec *cell_cache,
-                                                int cache_base, int img, FlowCtl *ctl)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const int G = d.G, h = d.h, W = d.W, G8 = (G + 7) / 8 * 8;
-    const int cp = l.cp_in;
-    const int c6 = l.constrain == 6 ? 1 : 0;
-    const int tc = step - ch.plane;
-    const int first = start[ch.plane];
-    const bool live = lane < 25;
-    const int kw = lane % 5, kh = (lane / 5) % 5;
-    int nk_tap = live ? tc + 4 - kh - kw + c6 : 0;
-    nk_tap = nk_tap > G ? G : (nk_tap < 0 ? 0 : nk_tap);
-    int gmax = tc + 4 + c6;
-    gmax = gmax > G ? G : gmax;
-    const float4 *wl_ = reinterpret_cast<const float4 *>(ws) + kh * 5 + kw;
-    for (int k0 = warp * C; k0 < ch.ncell; k0 += nwarp * C) {
-        const float *pa[C], *pb[C];
-        float tt[C];
-        int mode[C], nk[C];
-        i64 o[C];
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-            const int k = k0 + c;
-            pa[c] = pb[c] = l.in;
-            tt[c] = 0.f;
-            mode[c] = 3;
-            o[c] = 0;
-            if (k < ch.ncell) {
-                int pn, tw, g, th;
-                StepTapOff to;
-                to.offa = to.offb = 0; to.t = 0.f; to.mode = 3;
-                if (cache_base + k < STEP_CACHE_CELLS) {
-                    const StepCellRec cr = cell_cache[cache_base + k];
-                    pn = cr.pn; g = cr.g; th = cr.th; tw = cr.tw;
-                    if (live) to = tap_cache[(cache_base + k) * 25 + lane];
-                } else {
-                    pn = ch.net * d.nimg + img;
-                    const int4 ci = d.cell[first + ch.rem0 + k];
-                    tw = ci.x; g = ci.z; th = ci.w;
-                    if (live) to = step_resolve_off(d, pn, g, th + kh - 2, tw + kw - 2);
-                }
-                pa[c] = l.in + (i64)to.offa * cp;
-                pb[c] = l.in + (i64)to.offb * cp;
-                tt[c] = to.t;
-                mode[c] = to.mode;
-                o[c] = ((((i64)pn * d.npart + g) * (h + 2 * l.pad_out) + th + l.pad_out) * (W + 2 * l.pad_out) + tw + l.pad_out) * l.cp_out + tc;
-            }
-            nk[c] = mode[c] == 3 ? 0 : nk_tap;
-        }
-        float acc[C][GI][3];
-#pragma unroll
-        for (int c = 0; c < C; c++)
-#pragma unroll
-            for (int m = 0; m < GI; m++) acc[c][m][0] = acc[c][m][1] = acc[c][m][2] = 0.f;
-#pragma unroll
-        for (int m = 0; m < GI; m++) {
-            for (int c0 = 0; c0 < gmax; c0 += 8) {
-                float x[C][8];
-#pragma unroll
-                for (int c = 0; c < C; c++) {
-                    const int on = nk[c] > c0;
-                    float4 xa[2], xb[2];
-                    xa[0] = xa[1] = xb[0] = xb[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    ld_ca_v4x2(xa, pa[c] + m * G8 + c0, on && mode[c] != 2);
-                    ld_ca_v4x2(xb, pb[c] + m * G8 + c0, on && (mode[c] == 1 || mode[c] == 2));
-                    float va[8] = {xa[0].x, xa[0].y, xa[0].z, xa[0].w, xa[1].x, xa[1].y, xa[1].z, xa[1].w};
-                    if (on && nk[c] <= c0 + 8 && mode[c] != 2) flow_validate<1>(va, nk[c] - 1 - c0, pa[c] + m * G8 + nk[c] - 1, ctl);
-                    if (mode[c] != 0) {
-                        float vb[8] = {xb[0].x, xb[0].y, xb[0].z, xb[0].w, xb[1].x, xb[1].y, xb[1].z, xb[1].w};
-                        if (on && nk[c] <= c0 + 8 && mode[c] != 4) flow_validate<1>(vb, nk[c] - 1 - c0, pb[c] + m * G8 + nk[c] - 1, ctl);
-#pragma unroll
-                        for (int e = 0; e < 8; e++) va[e] = lerp2_ref(va[e], vb[e], tt[c]);
-                    }
-#pragma unroll
-                    for (int e = 0; e < 8; e++) x[c][e] = va[e];
-                }
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    if (c0 + u < nk_tap) {
-                        const float4 w = wl_[((c0 + u) * GI + m) * 25];          // one weight load, C cells
-#pragma unroll
-                        for (int c = 0; c < C; c++) {
-                            if (c0 + u < nk[c]) {
-                                acc[c][m][0] = __fmaf_rn(x[c][u], w.x, acc[c][m][0]);
-                                acc[c][m][1] = __fmaf_rn(x[c][u], w.y, acc[c][m][1]);
-                                acc[c][m][2] = __fmaf_rn(x[c][u], w.z, acc[c][m][2]);
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        // per cell: the reference's fold ([t] += [t+64], [t] += [t+32], shuffle-down 16 .. 1), bias, PReLU, residual, store
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-            const bool valid = k0 + c < ch.ncell;                 // warp-uniform
-            float addv = 0.f;
-            if (valid && l.add != nullptr && lane < 3) addv = flow_ld(l.add + o[c] + lane * G8);
-            float sum[3];
-#pragma unroll
-            for (int og = 0; og < 3; og++) {
-                float v0, v1 = 0.f, v2 = 0.f;
-                if (GI == 1) {
-                    v0 = acc[c][0][og];
-                } else {
-                    const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
-                    const float a0 = __shfl_sync(0xffffffffu, acc[c][0][og], i0 % 25);
-                    const float a1 = __shfl_sync(0xffffffffu, acc[c][GI > 1 ? 1 : 0][og], i0 % 25);
-                    v0 = i0 < 25 ? a0 : a1;
-                    const float b1 = __shfl_sync(0xffffffffu, acc[c][GI > 1 ? 1 : 0][og], i1 % 25);
-                    const float b2 = __shfl_sync(0xffffffffu, acc[c][GI > 2 ? 2 : 0][og], i1 % 25);
-                    v1 = i1 < 50 ? b1 : b2;
-                    const float c2 = __shfl_sync(0xffffffffu, acc[c][GI > 2 ? 2 : 0][og], i2 % 25);
-                    v2 = i2 < 75 ? c2 : 0.f;
-                }
-                const float s0 = __fadd_rn(v0, v2);
-                const float s1 = __fadd_rn(v1, 0.f);
-                sum[og] = __fadd_rn(s0, s1);
-            }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-                for (int og = 0; og < 3; og++) sum[og] = __fadd_rn(sum[og], __shfl_down_sync(0xffffffffu, sum[og], off));
-            if (valid && l.add != nullptr && lane < 3 && __float_as_uint(addv) == FLOW_SENTINEL) addv = flow_poll(l.add + o[c] + lane * G8, ctl);
-            const float add1 = __shfl_sync(0xffffffffu, addv, 1), add2 = __shfl_sync(0xffffffffu, addv, 2);
-            if (valid && lane == 0) {
-                const float adds[3] = {addv, add1, add2};
-#pragma unroll
-                for (int og = 0; og < 3; og++) {
-                    float v = __fadd_rn(sum[og], ws[4 * wstride + og]);
-                    if (l.act != nullptr && v < 0.f) v = __fmul_rn(v, ws[4 * wstride + 3 + og]);
-                    if (l.add != nullptr) v = __fadd_rn(v, adds[og]);
-                    __stcg(l.out + o[c] + og * G8, v);
-                }
-            }
-        }
-    }
-}
-
-// CW = cells per warp: 1 = the warp-per-cell form (step_conv_phase<GI, true>, scratch element (k, m) at k * gi + m; one image:
-// shortest task), > 1 = flow_conv_multi (scratch element at m * G8 + k; batches: weight loads shared by CW cells).
-template <int CW>
-__global__ void __launch_bounds__(STEP_THREADS) wave_flow_kernel(const __grid_constant__ FlowNet f)
+// Measured alternatives to the warp-per-cell task that are NOT in this file any more (bit-identical, all slower on the B200;
+// numbers in profiles/r2c_flow_task_probe.txt): four lanes per task, C = 2 / 3 cells per warp sharing the weight loads, a
+// member-major layout with the loads of member m + 1 issued under the FFMAs of member m, L1 prefetch of the next task's operands.
+__global__ void __launch_bounds__(STEP_THREADS, 2) wave_flow_kernel(const __grid_constant__ FlowNet f)
 {
     extern __shared__ __align__(16) float step_ws[];  // 2 buffers of 4 * wstride weights + 8 (bias, slope)
     const StepNet &d = f.net;
@@ -447,13 +298,8 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_flow_kernel(const __grid_co
                 __syncthreads();
                 const float *ws = step_ws + buf * wbuf;
                 const int cbase = ci < STEP_MAX_RUNS ? s_cache_base[ci] : STEP_CACHE_CELLS;
-                if (CW == 1) {
-                    if (d.L[L].gi == 1) step_conv_phase<1, true>(d, d.L[L], step, ch, start, ws, wstride, s_tap, s_cell, cbase, img, &ctl);
-                    else step_conv_phase<3, true>(d, d.L[L], step, ch, start, ws, wstride, s_tap, s_cell, cbase, img, &ctl);
-                } else {
-                    if (d.L[L].gi == 1) flow_conv_multi<1, CW>(d, d.L[L], step, ch, start, ws, wstride, s_tap, s_cell, cbase, img, &ctl);
-                    else flow_conv_multi<3, CW>(d, d.L[L], step, ch, start, ws, wstride, s_tap, s_cell, cbase, img, &ctl);
-                }
+                if (d.L[L].gi == 1) step_conv_phase<1, true>(d, d.L[L], step, ch, start, ws, wstride, s_tap, s_cell, cbase, img, &ctl);
+                else step_conv_phase<3, true>(d, d.L[L], step, ch, start, ws, wstride, s_tap, s_cell, cbase, img, &ctl);
                 if (restage) buf ^= 1;
             }
             if (tracer && L < 12) f.trace[(size_t)step * 16 + 2 + L] = flow_now();
@@ -470,14 +316,13 @@ __global__ void __launch_bounds__(STEP_THREADS) wave_flow_kernel(const __grid_co
                 const int4 ci = d.cell[first + k];
                 const int tw = ci.x, hp = ci.y, g = ci.z, th = ci.w;
                 const int tc = step - tw - hp;
-                const int es = CW == 1 ? 1 : (G + 7) / 8 * 8;       // stride of the three outputs of a channel group in the scratch layout
-                const float *pp = last.out + ((((i64)img * d.npart + g) * h + th) * W + tw) * last.cp_out + (CW == 1 ? tc * 3 : tc);
+                const float *pp = last.out + ((((i64)img * d.npart + g) * h + th) * W + tw) * last.cp_out + tc * 3;
                 float v[9];
 #pragma unroll
-                for (int j = 0; j < 9; j++) v[j] = flow_ld(pp + (j / 3) * net_stride + (j % 3) * es);   // nets: logits, delta, mean
+                for (int j = 0; j < 9; j++) v[j] = flow_ld(pp + (j / 3) * net_stride + (j % 3));   // nets: logits, delta, mean
 #pragma unroll
                 for (int j = 0; j < 9; j++)
-                    if (__float_as_uint(v[j]) == FLOW_SENTINEL) v[j] = flow_poll(pp + (j / 3) * net_stride + (j % 3) * es, &ctl);
+                    if (__float_as_uint(v[j]) == FLOW_SENTINEL) v[j] = flow_poll(pp + (j / 3) * net_stride + (j % 3), &ctl);
                 float w[3] = {v[0], v[1], v[2]}, dl[3] = {v[3], v[4], v[5]}, mu[3] = {v[6], v[7], v[8]}, c[9];
                 gmm_cdf_row<3, 8>(w, dl, mu, 3, 8, d.gmm_bias, d.gmm_total, d.gmm_beta, 0, c);
                 uint4 r;
@@ -567,17 +412,12 @@ int pcx_wave_decode_flow(const pcx_wave_net &n, pcx_coder *const *coders, long l
 
     const int threads = STEP_THREADS;
     const size_t smem = sizeof(float) * 2 * (4 * (size_t)n.G * 3 * 25 + 8);
-    // cells per warp: 1 for one or two images (latency), 2 for batches (throughput); PCX_FLOW_CW = 1 / 2 / 3 overrides
-    int cw = 1;
-    if (const char *e = getenv("PCX_FLOW_CW")) cw = atoi(e) >= 1 && atoi(e) <= 3 ? atoi(e) : cw;
-    const void *kernel = cw == 1 ? (const void *)wave_flow_kernel<1> : (cw == 2 ? (const void *)wave_flow_kernel<2> : (const void *)wave_flow_kernel<3>);
+    const void *kernel = (const void *)wave_flow_kernel;
     if (!st.attr_set) {
         int dev = 0;
         PCX_CUDA(cudaGetDevice(&dev));
         PCX_CUDA(cudaDeviceGetAttribute(&st.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        PCX_CUDA(cudaFuncSetAttribute(wave_flow_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, st.max_smem - 48 * 1024));
-        PCX_CUDA(cudaFuncSetAttribute(wave_flow_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, st.max_smem - 48 * 1024));
-        PCX_CUDA(cudaFuncSetAttribute(wave_flow_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, st.max_smem - 48 * 1024));
+        PCX_CUDA(cudaFuncSetAttribute(wave_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st.max_smem - 48 * 1024));
         st.attr_set = true;
     }
     int per_sm = 0;
@@ -593,7 +433,7 @@ int pcx_wave_decode_flow(const pcx_wave_net &n, pcx_coder *const *coders, long l
     int maxcount = 1;
     std::vector<int4> sched(nsteps);
     std::vector<int> counts(nsteps);
-    const int wpb = threads / 32 * cw;                           // cells a block works on at a time
+    const int wpb = threads / 32;
     for (int step = 0; step < nsteps; step++) {
         int p0 = step - n.G + 1 < 0 ? 0 : step - n.G + 1;
         int p1 = step < nplanes - 1 ? step + 1 : nplanes;         // planes [p0, p1) (entropy_conv_cuda_v2.cu:389-391)
