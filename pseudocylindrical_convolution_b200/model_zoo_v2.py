@@ -71,9 +71,27 @@ class _Block(nn.Module):
         self.npart = npart
         self._ctx = [ctx]          # shared geometry object, deliberately not registered as a submodule
         self._nhwc = [None]
+        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module.refresh())
 
     def wl(self, x, h, W):
         return _widths(self._ctx[0], x, h, W)
+
+    def refresh(self):
+        """Drop everything derived from the parameters: packed TF32 weights, GDN beta' / gamma', the captured CUDA graph.  The
+        caches key on Tensor._version, which in-place updates through `.data` (a common idiom, also in checkpoint surgery) do
+        not bump: call this after such an edit.  load_state_dict() and .to() / .cuda() call it through the hooks below."""
+        self.__dict__.pop("_pcx_graph", None)
+        for m in self.modules():
+            if isinstance(m, _Block) and m._nhwc[0] is not None:
+                m._nhwc[0]._packed.clear()
+            if hasattr(m, "_eff"):
+                m._eff = None
+        return self
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.refresh()
+        return out
 
     def _runner(self):
         """channels-last / tensor-core executor of this transform (transforms_nhwc.Runner), created on first use"""
@@ -230,10 +248,14 @@ class ResidualBlockUp(_Block):
         h, W = x.shape[2:]
         wl = self.wl(x, h, W)
         wl2 = self.wl(x, 2 * h, 2 * W)
-        br1 = pconv(self.pad1(x), self.conv1, self.npart, wl, prelu=self.relu1)
+        # The reference does not trim conv1 / short_cut before Dtow (:166-173), and round-half-up band widths do not always double
+        # (code width 104 -> 208: band 0 has 24 -> 49 columns): the last valid up-sampled column then comes from conv column
+        # wl[g], one beyond the band.  Keep every column the up-sampled band needs.
+        wl_up = [min(W, max(int(a), (int(b) + 1) // 2)) for a, b in zip(wl, wl2)]
+        br1 = pconv(self.pad1(x), self.conv1, self.npart, wl_up, prelu=self.relu1)
         br1 = self.dtow1(br1)
         br1 = pconv(self.pad2(br1), self.conv2, self.npart, wl2)
-        br2 = self.dtow2(pconv(x, self.short_cut, self.npart, wl))
+        br2 = self.dtow2(pconv(x, self.short_cut, self.npart, wl_up))
         return self.relu2(br1, residual=br2)
 
 

@@ -449,3 +449,26 @@ def test_one_shot_encoder_variants_emit_identical_streams(codec, tmp_path):
     assert lib.pcx_wave_set_option(b"nonsense", 1) < 0
     got = dec.ent.decode_batch(H // 128, W // 8, [str(tmp_path / "default.bin")])
     assert torch.equal(got, sym)
+
+
+def test_refresh_after_data_edit(codec):
+    """Parameter edits through `.data` do not bump Tensor._version, which the packed-weight / GDN / CUDA-graph caches key on:
+    `refresh()` (also run by load_state_dict and .to()) must make the next pass use the new values."""
+    import torch
+    enc, dec, x, _ = codec
+    for _ in range(3):
+        ref = enc.latent(x).clone()                                # eager, capture, replay
+    wt = enc.encoder.net[9].weight
+    saved = wt.data.clone()
+    try:
+        wt.data.mul_(0.5)                                          # invisible to the version stamps
+        enc.encoder.refresh()
+        got = enc.latent(x).clone()
+        assert not torch.equal(got, ref), "stale packed weights / graph after refresh()"
+        sd = {k: v.clone() for k, v in enc.encoder.state_dict().items()}
+        sd["net.9.weight"] = saved
+        enc.encoder.load_state_dict(sd)                            # the post hook refreshes
+        assert torch.equal(enc.latent(x), ref)
+    finally:
+        wt.data.copy_(saved)
+        enc.encoder.refresh()

@@ -81,6 +81,28 @@ def test_synthesis_transform_vs_cpu_port(both, cuda):
     assert np.abs(other - tc).max() > 1e-3
 
 
+def test_widths_that_do_not_double(both, cuda):
+    """W = 1664: the code is 104 columns wide and the round-half-up band widths do not double from scale to scale (band 0: 24 ->
+    49 -> ...).  The reference leaves the convolutions in front of Dtow untrimmed (model_zoo_v2.py:166-173), so the last valid
+    up-sampled column comes from one column beyond the coarse band; both product paths must follow (the port does, literally)."""
+    import torch
+    enc, dec, cpu, _ = both
+    Hs, Ws = 256, 1664
+    assert [int(v) for v in cpu.wl(1, Ws // 16)][:2] == [24, 50] and [int(v) for v in cpu.wl(2, Ws // 8)][0] == 49
+    x = smooth_images(1, 3, Hs, Ws, seed=6)
+    sym = cpu.symbols(x)
+    want = cpu.reconstruct(sym)
+    st = torch.from_numpy(sym).to(cuda)
+    fp32 = _with_impl(1, lambda: dec.reconstruct(st).cpu().numpy())
+    tc = _with_impl(0, lambda: dec.reconstruct(st).cpu().numpy())
+    assert np.abs(fp32 - want).max() < 1e-3, np.abs(fp32 - want).max()
+    assert np.abs(tc - want).max() < 5e-2, np.abs(tc - want).max()
+    lat = cpu.analysis(x)
+    xt = torch.from_numpy(x).to(cuda)
+    assert np.abs(_with_impl(1, lambda: enc.latent(xt).cpu().numpy()) - lat).max() < 2e-4
+    assert np.abs(_with_impl(0, lambda: enc.latent(xt).cpu().numpy()) - lat).max() < 2e-2
+
+
 @pytest.mark.parametrize("Hs,Ws", [(1024, 2048), (2048, 4096)])
 def test_large_image_round_trip(both, cuda, tmp_path, Hs, Ws):
     """Sizes beyond the reference's hard-wired 512x1024 (pseudo_codec.py:206-209): one-shot encoder with automatic slabs,
