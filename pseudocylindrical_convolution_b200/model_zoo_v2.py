@@ -65,13 +65,17 @@ class ClipData(nn.Module):
         return torch.where(x < 0, x * 0.01, torch.where(x > 1, 1 + (x - 1) * 0.01, x))
 
 
+def _refresh_hook(module, incompatible_keys):
+    module.refresh()               # (a post hook must return None)
+
+
 class _Block(nn.Module):
     def __init__(self, npart, ctx):
         super().__init__()
         self.npart = npart
         self._ctx = [ctx]          # shared geometry object, deliberately not registered as a submodule
         self._nhwc = [None]
-        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module.refresh())
+        self.register_load_state_dict_post_hook(_refresh_hook)
 
     def wl(self, x, h, W):
         return _widths(self._ctx[0], x, h, W)
@@ -297,5 +301,19 @@ class DecoderV2(_Block):
         for i in range(10):
             x = self.net[i](x)
         h, W = x.shape[2:]
-        y = pconv(self.net[10](x), self.net[11], self.npart, self.wl(x, h, W))
+        wl, wl2 = self.wl(x, h, W), self.wl(x, 2 * h, 2 * W)
+        wl_up = [min(W, max(int(a), (int(b) + 1) // 2)) for a, b in zip(wl, wl2)]      # untrimmed before Dtow, as in ResidualBlockUp
+        y = pconv(self.net[10](x), self.net[11], self.npart, wl_up)
         return self.net[12](y)
+
+    def widths_double(self, x_like, h, W):
+        """True when, at every up-sampling stage of this transform, no band is wider than twice its width one scale below.
+        The channels-last path keeps its wrap columns inside the activation buffers and therefore cannot reproduce the
+        reference's untrimmed column beyond the band; such image widths (not multiples of 1024, e.g. 1664) run the exact
+        NCHW path (PseudoDecoder.reconstruct)."""
+        for _ in range(4):
+            a, b = self.wl(x_like, h, W), self.wl(x_like, 2 * h, 2 * W)
+            if any(int(q) > 2 * int(p) for p, q in zip(a, b)):
+                return False
+            h, W = 2 * h, 2 * W
+        return True

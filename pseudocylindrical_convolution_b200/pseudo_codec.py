@@ -273,7 +273,7 @@ class PseudoDecoder(nn.Module):
             code_f = torch.zeros((n, self.code_channels, h, w)).type_as(code_ext)
             code_f[:, :self.valid_dim] = code_ext
             from . import config
-            if config.CONV_IMPL == 1:
+            if config.CONV_IMPL == 1 or not self.decoder.widths_double(code_f, h, w):
                 tx = self.uslice(self.decoder(code_f.contiguous()))
             else:
                 from .transforms_nhwc import decoder_forward

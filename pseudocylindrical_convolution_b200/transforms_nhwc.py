@@ -245,8 +245,7 @@ def _residual_block_up(R: Runner, m, X: View):
     wl = R.widths(X.h, X.W)
     h2, W2 = 2 * X.h, 2 * X.W
     wl2 = R.widths(h2, W2)
-    # the reference does not trim before Dtow and band widths do not always double (see model_zoo_v2.ResidualBlockUp)
-    wl = [min(X.W, max(int(a), (int(b) + 1) // 2)) for a, b in zip(wl, wl2)]
+    assert all(int(b) <= 2 * int(a) for a, b in zip(wl, wl2)), "widths that do not double take the NCHW path (DecoderV2.widths_double)"
     ch = X.C
     fused = 4 * ch == m.conv1.out_channels and ch in (96, 192)      # Dtow folded into the convolutions' stores (impl 3)
     if fused:
