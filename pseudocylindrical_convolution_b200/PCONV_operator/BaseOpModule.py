@@ -1,10 +1,13 @@
-"""Device plumbing shared by the operator modules (reference: PCONV_operator/BaseOpModule.py:5-54).
+"""Device bookkeeping shared by the operator modules.
 
-A module keeps one native op object per GPU id in `self.op`; moving the module re-keys the entry and tells the
-native object (`op.to(id)`), exactly like the reference.  nn.DataParallel replication shares the op table.
+Contract kept from the reference (PCONV_operator/BaseOpModule.py:5-54): a module owns one native op object per GPU id in the
+dict `self.op`; moving the module to another GPU (`.to('cuda:1')`, `.cuda(1)`) re-keys its single entry and tells the native
+object (`op.to(id)`); `device_list` records the ids it was built for; replicas made by nn.DataParallel share the op table.
+
+How it is done here: nn.Module funnels every move through `_apply(fn)`.  Instead of posing as a tensor, the module asks `fn` where
+it sends things by passing it an empty probe tensor, and follows when the answer is a CUDA device.
 """
-from collections import OrderedDict
-
+import torch
 from torch import nn
 
 
@@ -12,54 +15,38 @@ class BaseOpModule(nn.Module):
 
     def __init__(self, devices=0):
         super().__init__()
-        self.device_list = [devices] if isinstance(devices, int) else list(devices)
-        self.apply_flag = False
+        self.device_list = [devices] if isinstance(devices, int) else [int(d) for d in devices]
 
-    # nn.Module.to() funnels through _apply(fn); remember that it ran so the custom to() can re-key the op
     def _apply(self, fn, *args, **kwargs):
         super()._apply(fn, *args, **kwargs)
-        self.apply_flag = True
-        fn(self)
+        target = self._target_gpu(fn)
+        if target is not None:
+            self._follow(target)
         return self
 
-    def custom_op_replicate(self, other):
-        other.op = self.op
-        return other
-
-    def _replicate_for_data_parallel(self):
-        replica = self.custom_op_replicate(self.__new__(type(self)))
-        replica.__dict__ = self.__dict__.copy()
-        replica._parameters = OrderedDict()
-        replica._buffers = replica._buffers.copy()
-        replica._modules = replica._modules.copy()
-        replica._is_replica = True
-        return replica
-
-    def custom_op_to(self, *args):
-        if args and args[0] is not None and getattr(args[0], "index", None) is not None and len(self.op) == 1:
-            new_id, old_id = args[0].index, next(iter(self.op))
-            if new_id != old_id:
-                self.op[new_id] = self.op.pop(old_id)
-                self.op[new_id].to(new_id)
-
-    # fn(self) above calls these on the module itself (torch probes tensors this way)
-    def is_floating_point(self):
-        return False
-
-    def is_complex(self):
-        return False
-
-    def to(self, *args, **kwargs):
-        if not self.apply_flag:
-            super().to(*args, **kwargs)
-        else:
-            self.custom_op_to(*args)
-            self.apply_flag = False
-        return self
-
-    # helper used by every wrapper: native op bound to the tensor's device
-    def native(self, x):
+    @staticmethod
+    def _target_gpu(fn):
+        """GPU index `fn` moves tensors to, or None (dtype casts, .cpu(), share_memory_() ...)"""
         try:
-            return self.op[x.device.index]
-        except KeyError:
-            raise RuntimeError("%s has no native op for %s (built for GPUs %s)" % (type(self).__name__, x.device, list(self.op)))
+            dev = fn(torch.empty(0)).device
+        except Exception:
+            return None
+        return dev.index if dev.type == "cuda" and dev.index is not None else None
+
+    def _follow(self, gpu):
+        ops = getattr(self, "op", None)
+        if not isinstance(ops, dict) or len(ops) != 1:      # built for several GPUs: every id keeps its own op
+            return
+        (old, op), = ops.items()
+        if old != gpu:
+            del ops[old]
+            ops[gpu] = op
+            op.to(gpu)
+            self.device_list = [gpu]
+
+    def native(self, x):
+        """the native op bound to the device of tensor x"""
+        op = self.op.get(x.device.index)
+        if op is None:
+            raise RuntimeError("%s has no native op for %s (built for GPUs %s)" % (type(self).__name__, x.device, sorted(self.op)))
+        return op
