@@ -221,7 +221,7 @@ class PseudoEncoder(nn.Module):
 
     def code(self, x):
         """ERP image -> (dequantised code, symbols)"""
-        with torch.no_grad():
+        with torch.no_grad(), torch.cuda.device(x.device):
             return self.quant(self.latent(x))
 
     def forward(self, x, code_name):
@@ -266,7 +266,7 @@ class PseudoDecoder(nn.Module):
         self.ent = EntDecoder(self.valid_dim // 4, self.npart, opt, quant_levels, gid=device_id)
 
     def reconstruct(self, hcode_i):
-        with torch.no_grad():
+        with torch.no_grad(), torch.cuda.device(hcode_i.device):
             code_i = self.wtd(hcode_i)
             code_ext = self.quant(code_i)
             n, _, h, w = code_ext.shape

@@ -326,13 +326,16 @@ def _run_graphed(owner, fn, x):
 
 
 def encoder_forward(enc, erp, slice_op):
-    """EncoderV2 + SphereSlice on an ERP batch; graph-replayed from the third call with the same problem (see above)."""
-    return _run_graphed(enc, lambda t: _encoder_forward(enc, t, slice_op), erp)
+    """EncoderV2 + SphereSlice on an ERP batch; graph-replayed from the third call with the same problem (see above).
+    Runs with the input's GPU as the current device (streams, allocations and launches follow the tensor, not the caller)."""
+    with torch.cuda.device(erp.device):
+        return _run_graphed(enc, lambda t: _encoder_forward(enc, t, slice_op), erp)
 
 
 def decoder_forward(dec, code, uslice_op):
     """DecoderV2 + SphereUslice; graph-replayed from the third call with the same problem (see above)."""
-    return _run_graphed(dec, lambda t: _decoder_forward(dec, t, uslice_op), code)
+    with torch.cuda.device(code.device):
+        return _run_graphed(dec, lambda t: _decoder_forward(dec, t, uslice_op), code)
 
 
 @torch.no_grad()
