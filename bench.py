@@ -382,7 +382,10 @@ def run_gpu(args):
             s_.record()
             r = orig_call(name, *a)
             e_.record()
-            conv_ev.append((s_, e_))
+            d = a[0]._obj                                   # the ConvDesc of this launch: shape class + FLOPs on the valid cells
+            cols = sum(min(int(d.wl_out[g]), int(d.Wo)) for g in range(int(d.npart)))
+            flops = 2.0 * d.k * d.k * d.Ci * d.Co * d.N * d.Ho * cols
+            conv_ev.append((s_, e_, (int(d.k), int(d.stride), int(d.Ci), int(d.Co)), flops))
             return r
         return orig_call(name, *a)
 
@@ -433,15 +436,32 @@ def run_gpu(args):
     dec_v = sharding.job_throughput(mp_step, sum(dec_s) / len(dec_s), dev)[0]
     bpp = sum(os.path.getsize(n) for n in names) * 8.0 / (nimg * H * W)
     finite = bool(torch.isfinite(rec).all())
-    conv_ms = sum(a.elapsed_time(b) for a, b in conv_ev) / max(1, args.steps)           # per step, all conv launches
+    conv_ms = sum(e[0].elapsed_time(e[1]) for e in conv_ev) / max(1, args.steps)        # per step, all conv launches
+    classes = {}
+    for e in conv_ev:
+        c = classes.setdefault(e[2], [0.0, 0.0, 0])
+        c[0] += e[0].elapsed_time(e[1])
+        c[1] += e[3]
+        c[2] += 1
     tnh.call = orig_call
     config.CUDA_GRAPHS = graphs_before
     flops_step = (FLOP_PER_PX_ENC + FLOP_PER_PX_DEC) * nimg * H * W
     tf32_peak = peaks["bf16_sustained"] / 2.0
-    roofline = None
+    roofline = roofline_all = None
     if conv_ev:
         tfl = flops_step / (conv_ms / 1e3) / 1e12
-        roofline = {"kernel": "transform convolutions: conv_pair_kernel / conv_tc_kernel (tcgen05 kind::tf32, TMEM accumulators), %d launches per step" % (len(conv_ev) // args.steps),
+        # the dominant tensor kernel of the step: the 3x3 stride-1 192 -> 192 layers = conv_pair_kernel<192> (CTA pairs, halo-tile taps)
+        main = classes.get((3, 1, 192, 192))
+        if main:
+            m_tfl = main[1] / (main[0] / 1e3) / 1e12
+            roofline = {"kernel": "conv_pair_kernel<192> (tcgen05 cta_group::2 kind::tf32, TMEM accumulators): the 3x3 stride-1 192->192 layers of both transforms, %d launches per step" % (main[2] // args.steps),
+                        "bound": "tensor", "achieved": m_tfl, "peak": tf32_peak, "unit": "TFLOP/s", "frac": m_tfl / tf32_peak, "traffic": None,
+                        "peak_source": "%s bf16_tflops_sustained / 2 (kind::tf32 issues at half the f16 rate)" % peaks["source"],
+                        "peak_burst": peaks["bf16"] / 2.0, "flops_per_step": main[1] / args.steps, "ms_per_step": main[0] / args.steps,
+                        "share_of_conv_time": main[0] / sum(c[0] for c in classes.values()), "share_of_step": main[0] / args.steps / (sec_rank * 1e3),
+                        "note": "FLOPs on the valid cells of every launch (from its ConvDesc) / summed CUDA-event time of those launches in the timed steps; at 512x1024 x %d "
+                                "images the deepest scales are 2 x 64 and 4 x 128 tiles per band, far from the 1.01 the same kernel reaches on configs[1] (tile_pipeline.conv)" % nimg}
+        roofline_all = {"kernel": "all transform convolutions: conv_pair_kernel / conv_tc_kernel (tcgen05 kind::tf32, TMEM accumulators), %d launches per step" % (len(conv_ev) // args.steps),
                     "bound": "tensor", "achieved": tfl, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tfl / tf32_peak,
                     "traffic": None, "peak_source": "%s bf16_tflops_sustained / 2 (kind::tf32 issues at half the f16 rate)" % peaks["source"],
                     "peak_burst": peaks["bf16"] / 2.0, "flops_per_step": flops_step, "conv_ms_per_step": conv_ms,
@@ -534,7 +554,8 @@ def run_gpu(args):
                            "l2": "256 MB buffer rewritten before every step; per-step activations (~1 GB per layer) exceed the 126 MB L2",
                            "parallelism": "image-sharded x%d, no collective" % world, "cuda_graphs": bool(nimg < 4 and graphs_before)},
                 "encode_MP/s": enc_v, "decode_MP/s": dec_v, "bpp": bpp, "roundtrip_symbols_identical": roundtrip_ok, "reconstruction_finite": finite,
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_latency": roofline_latency,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_all_convs": roofline_all,
+                "roofline_latency": roofline_latency,
                 "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "stages": stages, "large_configs": extras, "tile_pipeline": tile}
         print(json.dumps(line))
     if world > 1:
