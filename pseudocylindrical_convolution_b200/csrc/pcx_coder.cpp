@@ -431,9 +431,14 @@ int pcx_coder_decodes_rows16(pcx_coder *c, const uint16_t *rows, int n, unsigned
     uint64_t low = c->low, high = c->high, code = c->code;
     if (low >= high || (low & kMask) != low || (high & kMask) != high || high - low + 1 < kMinRange) { pcx_set_error("coder: low/high out of range"); return PCX_ECODER; }
     BitSource &src = c->source;
+    // the stream cursor lives in locals; every symbol consumes k + m bits (k leading agreeing bits, m underflow bits), both taken
+    // from ONE 64-bit window fetched at the top of the iteration - its address depends only on the cursor, so the load is off
+    // the serial chain range -> boundaries -> symbol -> low / high -> k -> m
+    const unsigned char *bytes = src.bytes.data();
+    const size_t last_window = src.nbytes + 8;                     // the vector carries 16 zero bytes behind the stream
+    uint64_t bitpos = src.bitpos;
     int rc = PCX_OK, i = 0;
     for (; i < n; i++) {
-        // one aligned 16-byte load: the row was written by a single 16-byte store, so the tag vouches for the boundaries
         // ONE 16-byte load, forced (a plain _mm_load_si128 is an ordinary dereference: the optimiser narrowed it into separate
         // loads and read the boundaries BEFORE the tag - a row landing in between was accepted with the previous step's
         // boundaries).  The device wrote the row with a single 16-byte store, so tag and boundaries are one snapshot.
@@ -442,6 +447,11 @@ int pcx_coder_decodes_rows16(pcx_coder *c, const uint16_t *rows, int n, unsigned
         uint16_t r[8];
         memcpy(r, &v, 16);
         if (r[7] != (uint16_t)tag16) break;
+        size_t byte = (size_t)(bitpos >> 3);
+        byte = byte < last_window ? byte : last_window;
+        uint64_t win;
+        memcpy(&win, bytes + byte, 8);
+        win = __builtin_bswap64(win) << (bitpos & 7);              // next 57 .. 64 bits of the stream, left-aligned
         const uint64_t range = high - low + 1, offset = code - low;
         uint64_t bnd[9];
         bnd[0] = 0;
@@ -460,16 +470,31 @@ int pcx_coder_decodes_rows16(pcx_coder *c, const uint16_t *rows, int n, unsigned
         high = low + bb - 1;
         low = low + ba;
         const int k = __builtin_clz((uint32_t)(low ^ high) | 1u);      // see pcx_coder_encodes: k <= 31, k = 0 / m = 0 are identities
-        code = ((code << k) & kMask) | src.get_bits(k);
         low = (low << k) & kMask;
         high = ((high << k) & kMask) | ((1ull << k) - 1ull);
         const uint32_t under = (uint32_t)(low & ~high) << 1;
         const int m = under == 0xffffffffu ? 31 : __builtin_clz(~under);
-        code = (code & kHalf) | ((code << m) & (kMask >> 1)) | src.get_bits(m);
+        uint64_t bits_k, bits_m;
+        if (__builtin_expect(k + m <= 56, 1)) {
+            bits_k = (win >> 1) >> (63 - k);                       // top k bits of the window (k = 0: none)
+            bits_m = ((win << k) >> 1) >> (63 - m);                // the next m bits
+        } else {                                                   // more than one window's worth: fetch the m bits separately
+            bits_k = (win >> 1) >> (63 - k);
+            size_t byte2 = (size_t)((bitpos + (uint64_t)k) >> 3);
+            byte2 = byte2 < last_window ? byte2 : last_window;
+            uint64_t w2;
+            memcpy(&w2, bytes + byte2, 8);
+            w2 = __builtin_bswap64(w2) << ((bitpos + (uint64_t)k) & 7);
+            bits_m = (w2 >> 1) >> (63 - m);
+        }
+        bitpos += (uint64_t)(k + m);
+        code = ((code << k) & kMask) | bits_k;
+        code = (code & kHalf) | ((code << m) & (kMask >> 1)) | bits_m;
         low = (low << m) & (kMask >> 1);
         high = ((high << m) & (kMask >> 1)) | kHalf | ((1ull << m) - 1ull);
         __atomic_store_n(out_words + i, (word_tag << 8) | a, __ATOMIC_RELEASE);
     }
+    src.bitpos = bitpos;
     c->low = low; c->high = high; c->code = code;
     *done = i;
     return rc;
