@@ -366,7 +366,7 @@ struct StepCellRec { int pn, g, th, tw; };
 template <int GI, bool FLOW = false>
 __device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLayer &l, int step, const StepChunk &ch, const int *start,
                                                 const float *ws, int wstride, const StepTapOff *tap_cache, const StepCellRec *cell_cache,
-                                                int cache_base, int img_base = 0, FlowCtl *ctl = nullptr)
+                                                int cache_base, int img_base = 0, FlowCtl *ctl = nullptr, int cache_cells = STEP_CACHE_CELLS)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int G = d.G, h = d.h, W = d.W;
@@ -396,7 +396,7 @@ __device__ __forceinline__ void step_conv_phase(const StepNet &d, const StepLaye
         tp.pa = tp.pb = l.in;
         tp.t = 0.f;
         tp.mode = 3;
-        if (cache_base + k < STEP_CACHE_CELLS) {
+        if (cache_base + k < cache_cells) {
             const StepCellRec cr = cell_cache[cache_base + k];
             pn = cr.pn; g = cr.g; th = cr.th; tw = cr.tw;
             if (live) tp = step_tap_of(tap_cache[(cache_base + k) * 25 + lane], l.in, cp);

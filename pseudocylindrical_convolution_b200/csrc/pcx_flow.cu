@@ -141,7 +141,13 @@ __device__ __noinline__ unsigned flow_poll_symbol(const FlowNet &f, const unsign
 // Measured alternatives to the warp-per-cell task that are NOT in this file any more (bit-identical, all slower on the B200;
 // numbers in profiles/r2c_flow_task_probe.txt): four lanes per task, C = 2 / 3 cells per warp sharing the weight loads, a
 // member-major layout with the loads of member m + 1 issued under the FFMAs of member m, L1 prefetch of the next task's operands.
-__global__ void __launch_bounds__(STEP_THREADS, 2) wave_flow_kernel(const __grid_constant__ FlowNet f)
+// NT threads per block, BPS blocks per SM, the first CACHE cells of a block's step resolved in shared memory.  Two forms are
+// built: 256 x 2 (cache 64) when a layer of a step is about one task per warp (one small image: fewest blocks to rendezvous
+// per weight change), 128 x 4 (cache 32) when every warp has several tasks per layer (batches, large images): smaller blocks
+// couple fewer warps at the barrier that follows a weight change (entropy decode, ms, 256 x 2 -> 128 x 4: 8 x 512x1024 60.2 -> 55.9,
+// 16 x 512x1024 122.5 -> 111.5, 1 x 1024x2048 47.0 -> 46.3, 1 x 2048x4096 149.7 -> 146.9; 1 x 512x1024 18.3 -> 18.4).
+template <int NT, int BPS, int CACHE>
+__global__ void __launch_bounds__(NT, BPS) wave_flow_kernel(const __grid_constant__ FlowNet f)
 {
     extern __shared__ __align__(16) float step_ws[];  // 2 buffers of 4 * wstride weights + 8 (bias, slope)
     const StepNet &d = f.net;
@@ -157,8 +163,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 2) wave_flow_kernel(const __grid
     unsigned *ready = f.dev_ctl + 16 + img;
     __shared__ StepChunk s_chunk[STEP_MAX_RUNS];
     __shared__ int s_cache_base[STEP_MAX_RUNS + 1];
-    __shared__ StepCellRec s_cell[STEP_CACHE_CELLS];
-    __shared__ StepTapOff s_tap[STEP_CACHE_CELLS * 25];
+    __shared__ StepCellRec s_cell[CACHE];
+    __shared__ StepTapOff s_tap[CACHE * 25];
     __shared__ unsigned s_abort;
     const bool tracer = f.trace != nullptr && blockIdx.x == 0 && tid == 0;
 
@@ -192,10 +198,10 @@ __global__ void __launch_bounds__(STEP_THREADS, 2) wave_flow_kernel(const __grid
         }
         __syncthreads();
         {
-            // (cell, tap) geometry of the block's first STEP_CACHE_CELLS cells, once for all layers: warp per cell, lane per tap
+            // (cell, tap) geometry of the block's first CACHE cells, once for all layers: warp per cell, lane per tap
             const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
             const int nruns = nmy < STEP_MAX_RUNS ? nmy : STEP_MAX_RUNS;
-            const int ncached = s_cache_base[nruns] < STEP_CACHE_CELLS ? s_cache_base[nruns] : STEP_CACHE_CELLS;
+            const int ncached = s_cache_base[nruns] < CACHE ? s_cache_base[nruns] : CACHE;
             for (int c = warp; c < ncached; c += nwarp) {
                 int ci = 0;
                 while (ci + 1 < nruns && s_cache_base[ci + 1] <= c) ci++;
@@ -225,16 +231,16 @@ __global__ void __launch_bounds__(STEP_THREADS, 2) wave_flow_kernel(const __grid
                 float *out = const_cast<float *>(d.L[0].in);
                 const unsigned *words = f.symw + (size_t)img * f.rows_cap;
                 const unsigned tag = 0x800000u | ((f.tag_salt & 0x7fu) << 16) | ((unsigned)step & 0xffffu);      // step = (decoded step) + 1
-                for (int base = 0; base < pcount; base += 4 * STEP_THREADS) {
+                for (int base = 0; base < pcount; base += 4 * NT) {
                     unsigned w[4];
 #pragma unroll
                     for (int j = 0; j < 4; j++) {                  // four PCIe reads in flight per thread
-                        const int t = base + j * STEP_THREADS + tid;
+                        const int t = base + j * NT + tid;
                         w[j] = t < pcount ? ld_volatile_u32(words + t) : 0u;
                     }
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const int t = base + j * STEP_THREADS + tid;
+                        const int t = base + j * NT + tid;
                         if (t >= pcount) continue;
                         if ((w[j] >> 8) != tag) w[j] = flow_poll_symbol(f, words + t, tag);
                         const int4 ci = d.cell[pfirst + t];
@@ -281,25 +287,34 @@ __global__ void __launch_bounds__(STEP_THREADS, 2) wave_flow_kernel(const __grid
         if (tracer) f.trace[(size_t)step * 16 + 1] = flow_now();
 
         // ---- the masked layers: no barrier between them, consumers poll the scalars they need (step_conv_phase<GI, true>)
+        // Weight buffers: an item whose (layer, net, plane) equals the previous item's reuses the rows in place - no copy and NO
+        // block barrier, the warps of the block drift apart over such items.  Only an item with new rows costs one barrier: it
+        // says that every thread's copies have landed and - every warp having finished the previous item - that the OTHER buffer
+        // is free, so the rows of the next different item are staged right after it, under this item's arithmetic.
         int it = 0, buf = 0;
+        bool fresh = true;                                 // the current buffer was filled since the last barrier
         for (int L = 0; L < d.nlayers; L++) {
             for (int ci = 0; ci < nmy; ci++, it++) {
                 const StepChunk ch = ci < STEP_MAX_RUNS ? s_chunk[ci] : step_chunk_of(start, c_first + ci, p0, np, S, d.nb, 1);
-                if (it > 0) __syncthreads();           // every warp is done with item it-1: the other weight buffer may be refilled
+                if (fresh) {
+                    cp_async_wait<0>();
+                    __syncthreads();
+                }
                 bool restage = false;
                 if (it + 1 < nitems) {
                     const int nci = ci + 1 < nmy ? ci + 1 : 0, nL = ci + 1 < nmy ? L : L + 1;
                     const StepChunk nc = nci < STEP_MAX_RUNS ? s_chunk[nci] : step_chunk_of(start, c_first + nci, p0, np, S, d.nb, 1);
-                    restage = nL != L || nc.net != ch.net || nc.plane != ch.plane;       // same rows: the next run reuses this buffer
-                    if (restage) flow_stage_packed(d, f.packed, wbuf, nL, nc.net, step - nc.plane, step_ws + (buf ^ 1) * wbuf);
+                    restage = nL != L || nc.net != ch.net || nc.plane != ch.plane;
+                    if (restage) {
+                        flow_stage_packed(d, f.packed, wbuf, nL, nc.net, step - nc.plane, step_ws + (buf ^ 1) * wbuf);
+                        cp_async_commit();
+                    }
                 }
-                cp_async_commit();
-                cp_async_wait<1>();                    // this item's rows have landed; the next item's may still be in flight
-                __syncthreads();
                 const float *ws = step_ws + buf * wbuf;
-                const int cbase = ci < STEP_MAX_RUNS ? s_cache_base[ci] : STEP_CACHE_CELLS;
-                if (d.L[L].gi == 1) step_conv_phase<1, true>(d, d.L[L], step, ch, start, ws, wstride, s_tap, s_cell, cbase, img, &ctl);
-                else step_conv_phase<3, true>(d, d.L[L], step, ch, start, ws, wstride, s_tap, s_cell, cbase, img, &ctl);
+                const int cbase = ci < STEP_MAX_RUNS ? s_cache_base[ci] : CACHE;
+                if (d.L[L].gi == 1) step_conv_phase<1, true>(d, d.L[L], step, ch, start, ws, wstride, s_tap, s_cell, cbase, img, &ctl, CACHE);
+                else step_conv_phase<3, true>(d, d.L[L], step, ch, start, ws, wstride, s_tap, s_cell, cbase, img, &ctl, CACHE);
+                fresh = restage;
                 if (restage) buf ^= 1;
             }
             if (tracer && L < 12) f.trace[(size_t)step * 16 + 2 + L] = flow_now();
@@ -312,7 +327,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 2) wave_flow_kernel(const __grid
             const StepLayer &last = d.L[d.nlayers - 1];
             const i64 net_stride = (i64)d.nimg * d.npart * h * W * last.cp_out;
             uint4 *rows = f.rows + (size_t)img * f.rows_cap;
-            for (int k = bi + B * tid; k < count; k += B * STEP_THREADS) {
+            for (int k = bi + B * tid; k < count; k += B * NT) {
                 const int4 ci = d.cell[first + k];
                 const int tw = ci.x, hp = ci.y, g = ci.z, th = ci.w;
                 const int tc = step - tw - hp;
@@ -354,9 +369,9 @@ struct FlowState {                  // per device, created on first use, guarded
     unsigned *h_symw = nullptr;     // mapped
     unsigned *h_ctl = nullptr;      // mapped
     size_t rows_cap_total = 0;
-    bool attr_set = false;
+    bool attr_set[2] = {false, false};  // per kernel form
     unsigned epoch = 1;
-    int max_smem = 0;
+    int max_smem[2] = {0, 0};
 };
 std::mutex g_states_mu;
 FlowState *g_states[64] = {nullptr};
@@ -410,18 +425,30 @@ int pcx_wave_decode_flow(const pcx_wave_net &n, pcx_coder *const *coders, long l
     FlowState &st = *stp;
     std::lock_guard<std::mutex> lock(st.mu);
 
-    const int threads = STEP_THREADS;
+    // ---- which form of the kernel: tasks of one layer of the widest step per warp of the 256 x 2 form
+    int widest = 1;
+    for (int step = 0; step < nsteps; step++) {
+        const int p0 = step - n.G + 1 < 0 ? 0 : step - n.G + 1, p1 = step < nplanes - 1 ? step + 1 : nplanes;
+        if (p1 > p0) widest = std::max(widest, n.h_start[p1] - n.h_start[p0]);
+    }
+    const long tasks_per_layer = (long)widest * n.nb * n.nimg;
+    int form = 2 * tasks_per_layer >= 3l * pcx_sm_count() * 16 ? 1 : 0;       // 1.5 or more tasks per warp and layer: small blocks
+    if (const char *e = getenv("PCX_FLOW_FORM")) form = atoi(e) == 1 ? 1 : 0;
+    const int threads = form == 1 ? 128 : 256;
     const size_t smem = sizeof(float) * 2 * (4 * (size_t)n.G * 3 * 25 + 8);
-    const void *kernel = (const void *)wave_flow_kernel;
-    if (!st.attr_set) {
-        int dev = 0;
+    const void *kernel = form == 1 ? (const void *)wave_flow_kernel<128, 4, 32> : (const void *)wave_flow_kernel<256, 2, 64>;
+    if (!st.attr_set[form]) {
+        int dev = 0, lim = 0;
         PCX_CUDA(cudaGetDevice(&dev));
-        PCX_CUDA(cudaDeviceGetAttribute(&st.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        PCX_CUDA(cudaFuncSetAttribute(wave_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st.max_smem - 48 * 1024));
-        st.attr_set = true;
+        PCX_CUDA(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        cudaFuncAttributes fa;
+        PCX_CUDA(cudaFuncGetAttributes(&fa, kernel));
+        st.max_smem[form] = lim - (int)fa.sharedSizeBytes - 1024;            // what is left for dynamic shared memory
+        PCX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st.max_smem[form]));
+        st.attr_set[form] = true;
     }
     int per_sm = 0;
-    if (smem > (size_t)(st.max_smem - 48 * 1024)) { *unsupported = true; return PCX_OK; }
+    if (smem > (size_t)st.max_smem[form]) { *unsupported = true; return PCX_OK; }
     PCX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     const int max_grid = pcx_sm_count() * per_sm;
     int B = n.nimg > 0 ? max_grid / n.nimg : 0;                  // blocks per image
