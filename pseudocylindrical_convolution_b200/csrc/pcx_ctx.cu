@@ -1294,6 +1294,14 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
     std::lock_guard<std::mutex> dev_lock(D.mu);
     rc = ensure_pinned(D, (size_t)n.cdf_rows, n.nstep);
     if (rc < 0) return rc;
+    // PCX_ENCODE_TRACE=1: wall-clock milestones on stderr (the stream is synchronised at each one: diagnosis only)
+    static const bool enc_trace = getenv("PCX_ENCODE_TRACE") != nullptr;
+    const auto trace_t0 = std::chrono::steady_clock::now();
+    auto trace_mark = [&](const char *what, bool sync) {
+        if (!enc_trace) return;
+        if (sync) cudaStreamSynchronize(s);
+        fprintf(stderr, "[pcx encode] %8.3f ms  %s\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - trace_t0).count(), what);
+    };
     PCX_CUDA(cudaMemcpyAsync(n.d_steptab, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, s));
 
     // ---- the network, layer by layer over the whole tensor
@@ -1460,6 +1468,7 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
         }
     }
     PCX_CUDA(cudaEventRecord(slab_ev[slab], s));
+    trace_mark("slab computed", true);
     }
 
     // ---- CDF rows in coding order, chunk by chunk, host coding pipelined behind the device
@@ -1468,14 +1477,18 @@ int pcx_wave_encode_full(const pcx_wave_net *net, const float *d_data, pcx_coder
     for (auto &e : ev) PCX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CoderPool pool;
     pool.start(coders, n.nimg, n.nstep, true);
+    trace_mark("coder threads started", false);
     int status = PCX_OK, per_chunk[2] = {0, 0}, s0 = 0, chunk = 0;
     long long total_rows = 0;
     auto code_chunk = [&](int b) -> int {
         cudaError_t e = cudaEventSynchronize(ev[b]);
         if (e != cudaSuccess) { pcx_set_error("cudaEventSynchronize -> %s", cudaGetErrorString(e)); return PCX_ECUDA; }
+        trace_mark("chunk on the host", false);
         if (per_chunk[b] <= 0) return PCX_OK;
         total_rows += (long long)per_chunk[b] * n.nimg;
-        return pool.run(D.pin.cdf[b], reinterpret_cast<int32_t *>(D.pin.lab[b]), nullptr, per_chunk[b]);
+        const int r = pool.run(D.pin.cdf[b], reinterpret_cast<int32_t *>(D.pin.lab[b]), nullptr, per_chunk[b]);
+        trace_mark("chunk coded", false);
+        return r;
     };
     int cur_slab = 0;
     while (s0 < nsteps && status == PCX_OK) {
