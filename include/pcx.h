@@ -168,6 +168,8 @@ typedef struct pcx_conv_desc {
     int aux_y0, aux_x0;
     int in_plane_rows;       /* physical rows between consecutive input planes (0 = Hi); lets d_x point INTO a padded buffer */
     int wl_out[PCX_MAX_PART];/* valid output width per band (columns >= wl_out are written as 0) */
+    int square_input;        /* 1: the convolution reads x * x (GDN / IGDN: beta' + gamma' x^2, PseudoContextV2.py:186-216) - squared on
+                              * chip, x^2 never exists in HBM; tensor-core path, k = 1, act 3 or 4 */
 } pcx_conv_desc;
 /* y = fill( residual + mul * act(conv(x) + bias) );  d_bias, d_slope, d_mul, d_residual may be NULL.
  * (AttentionBlock: x + t * sigmoid(conv1x1(.)), model_zoo_v2.py:73-76; ResidualBlock*: x + y, :49-53, :89-93) */

@@ -21,7 +21,8 @@ class ConvDesc(C.Structure):
     """struct pcx_conv_desc (include/pcx.h)."""
     _fields_ = [(n, C.c_int) for n in (
         "N", "npart", "Ci", "Hi", "in_pitch", "Co", "Ho", "Wo", "out_rows", "out_pitch", "out_y0", "out_x0",
-        "k", "stride", "act", "impl", "aux_rows", "aux_pitch", "aux_y0", "aux_x0", "in_plane_rows")] + [("wl_out", C.c_int * PCX_MAX_PART)]
+        "k", "stride", "act", "impl", "aux_rows", "aux_pitch", "aux_y0", "aux_x0", "in_plane_rows")] + [("wl_out", C.c_int * PCX_MAX_PART),
+                                                                                                          ("square_input", C.c_int)]
 
 
 class WaveLayer(C.Structure):

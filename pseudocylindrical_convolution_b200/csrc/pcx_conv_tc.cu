@@ -29,6 +29,7 @@ constexpr int UMMA_K = 8;             // tf32
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;     // 16 KB: 128 pixel rows x 128 B
 constexpr int NUM_THREADS = 192;      // 6 warps (CTA-pair kernel: 4 epilogue warps per CTA, 8 per pair)
 constexpr int TC_THREADS = 320;       // single-CTA kernel: producer, MMA issuer + EIGHT epilogue warps (two per TMEM lane quadrant)
+constexpr int SQ_WARPS = 2;           // + two warps that square the activation stage in place (GDN: the GEMM reads x^2)
 constexpr int MAX_CO_STAGED = 768;    // bias + PReLU slope vectors staged in shared memory (2 x 3 KB)
 constexpr int VEC_SMEM = 2 * MAX_CO_STAGED * 4 + 4 * 32 * 36 * 4;   // + the epilogue warps' transpose tiles
 
@@ -38,6 +39,7 @@ struct TcParams {
     int out_rows, out_pitch, out_y0, out_x0;
     int aux_rows, aux_pitch, aux_y0, aux_x0;
     int k, stride, act;
+    int square;             // 1: the GEMM reads x * x (squarer warps, conv_tc_kernel<.., SQ = true>)
     int d2w;                // 1: write the result depth-to-space (Dtow stride 2 fused into the store), GEMM column q*Co/4 + c = channel 4c + q
     int bw, bh;             // tile = bw columns x bh rows, bw * bh = 128
     int tiles_x, tiles_y, n_tiles, co_pad;
@@ -341,8 +343,13 @@ __device__ __forceinline__ void epilogue_warp(const TcParams &p, long long plane
     }
 }
 
-template <int NT, int ACTK>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap map_x,
+// SQ: the GEMM runs on x * x (GDN / IGDN, PseudoContextV2.py:186-216: beta' + gamma' x^2).  The round-1 form materialised x^2 in
+// HBM with its own kernel (one read + one write of the activation, then the GEMM read it back); here two extra warps square
+// each 16 KB activation stage IN SHARED MEMORY between the TMA's arrival and the MMA: same fp32 product, same tf32 operand,
+// no HBM traffic (two warps: 384 threads keep the 168 registers of the epilogue).  Pipeline per stage: TMA -> full_bar -> squarer warps (generic-proxy read-modify-write, fence.proxy.async) ->
+// sq_bar -> tcgen05.mma -> empty_bar.
+template <int NT, int ACTK, bool SQ = false>
+__global__ void __launch_bounds__(TC_THREADS + (SQ ? SQ_WARPS * 32 : 0), 1) conv_tc_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                   const __grid_constant__ CUtensorMap map_w, TcParams p,
                                                                   const float *__restrict__ bias, const float *__restrict__ slope,
                                                                   const float *__restrict__ mul, const float *__restrict__ residual,
@@ -357,7 +364,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint64_t *empty_bar = full_bar + C::STAGES;
     uint64_t *acc_full = empty_bar + C::STAGES;     // [2]
     uint64_t *acc_empty = acc_full + 2;             // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    uint64_t *sq_bar = acc_empty + 2;               // [STAGES] (SQ only): the stage's activations have been squared
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sq_bar + C::STAGES);
+    static_assert((3 * C::STAGES + 4) * 8 + 4 <= 256, "barrier block");
     float *s_bias = reinterpret_cast<float *>(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256);
     float *s_slope = s_bias + MAX_CO_STAGED;
     float *s_stage = s_slope + MAX_CO_STAGED;
@@ -372,6 +381,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int s = 0; s < C::STAGES; s++) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
+            mbar_init(&sq_bar[s], SQ_WARPS);
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(&acc_full[s], 1);
@@ -431,7 +441,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * NT;
                 for (int it = 0; it < iters; it++) {
-                    mbar_wait(&full_bar[stage], phase);
+                    mbar_wait(SQ ? &sq_bar[stage] : &full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_lo = lo0 + (uint32_t)stage * (C::STAGE_BYTES >> 4);
                     const uint32_t b_lo = a_lo + (A_STAGE_BYTES >> 4);
@@ -448,6 +458,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 }
                 umma_commit(&acc_full[acc]);                      // accumulator complete -> epilogue
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (SQ && warp >= TC_THREADS / 32) {
+        // ===================================================================================== squarer warps
+        const int tq = threadIdx.x - TC_THREADS;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            Tile tl = decode_tile(p, t);
+            if (!tile_live(p, tl)) continue;
+            for (int it = 0; it < iters; it++) {
+                mbar_wait(&full_bar[stage], phase);
+                float4 *a = reinterpret_cast<float4 *>(stage_base + (size_t)stage * C::STAGE_BYTES);
+#pragma unroll
+                for (int i = 0; i < A_STAGE_BYTES / 16 / (SQ_WARPS * 32); i++) {
+                    float4 v = a[tq + i * SQ_WARPS * 32];
+                    v.x = __fmul_rn(v.x, v.x); v.y = __fmul_rn(v.y, v.y); v.z = __fmul_rn(v.z, v.z); v.w = __fmul_rn(v.w, v.w);
+                    a[tq + i * SQ_WARPS * 32] = v;
+                }
+                fence_proxy_async();                              // generic-proxy stores -> the MMA's async-proxy operand reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sq_bar[stage]);
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else {
@@ -881,15 +914,15 @@ static long long pack_weights(const float *d_w, float *d_out, int Co, int Ci, in
     return total;
 }
 
-template <int NT, int ACTK>
+template <int NT, int ACTK, bool SQ = false>
 static int launch_tc_v(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, const float *bias, const float *slope,
                      const float *mul, const float *residual, float *y, cudaStream_t s)
 {
     using C = Cfg<NT>;
     static PcxDeviceOnce once;
-    PCX_ONCE_PER_DEVICE(once) PCX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT, ACTK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    PCX_ONCE_PER_DEVICE(once) PCX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT, ACTK, SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     long long grid = p.total_tiles < pcx_sm_count() ? p.total_tiles : pcx_sm_count();
-    conv_tc_kernel<NT, ACTK><<<(unsigned)grid, TC_THREADS, C::SMEM, s>>>(mx, mw, p, bias, slope, mul, residual, y);
+    conv_tc_kernel<NT, ACTK, SQ><<<(unsigned)grid, TC_THREADS + (SQ ? SQ_WARPS * 32 : 0), C::SMEM, s>>>(mx, mw, p, bias, slope, mul, residual, y);
     PCX_LAUNCHED();
     return PCX_OK;
 }
@@ -924,6 +957,10 @@ template <int NT>
 static int launch_tc(const CUtensorMap &mx, const CUtensorMap &mw, const TcParams &p, const float *bias, const float *slope,
                      const float *mul, const float *residual, float *y, cudaStream_t s)
 {
+    if (p.square) {         // GDN / IGDN layers only (pcx_conv2d_tc checks)
+        return p.act == 3 ? launch_tc_v<NT, 3, true>(mx, mw, p, bias, slope, mul, residual, y, s)
+                          : launch_tc_v<NT, 4, true>(mx, mw, p, bias, slope, mul, residual, y, s);
+    }
     switch (p.act) {
     case 2: return launch_tc_v<NT, 2>(mx, mw, p, bias, slope, mul, residual, y, s);
     case 3: return launch_tc_v<NT, 3>(mx, mw, p, bias, slope, mul, residual, y, s);
@@ -993,6 +1030,7 @@ int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w,
         if (rc < 0) return (int)rc;
     }
 
+    PCX_REQUIRE(d.square_input == 0 || (d.k == 1 && (d.act == 3 || d.act == 4)), "square_input is the GDN / IGDN form: 1x1, act 3 or 4 (k=%d act=%d)", d.k, d.act);
     const bool pair = pair_mode() != 0 && d.k == 3 && d.stride == 1 && d.Wo >= 64 && d.act <= 1 && d_mul == nullptr;
     const cuuint64_t plane_rows = (cuuint64_t)(d.in_plane_rows > 0 ? d.in_plane_rows : d.Hi);
 
@@ -1036,6 +1074,7 @@ int pcx_conv2d_tc(const pcx_conv_desc *desc, const float *d_x, const float *d_w,
     p.out_rows = d.out_rows; p.out_pitch = d.out_pitch; p.out_y0 = d.out_y0; p.out_x0 = d.out_x0;
     p.aux_rows = d.aux_rows; p.aux_pitch = d.aux_pitch; p.aux_y0 = d.aux_y0; p.aux_x0 = d.aux_x0;
     p.k = d.k; p.stride = d.stride; p.act = d.act;
+    p.square = d.square_input;
     p.d2w = d.impl == 3 ? 1 : 0;
     p.bw = bw; p.bh = bh;
     p.tiles_x = (d.Wo + bw - 1) / bw;

@@ -217,6 +217,8 @@ int pcx_conv2d_fwd(const pcx_conv_desc *desc, const float *d_x, const float *d_w
     PCX_REQUIRE(d.act <= 2 || d.impl != 1, "act %d (rsqrt / sqrt) is implemented by the tensor-core path only", d.act);
     PCX_REQUIRE(d.in_plane_rows == 0 || (d.in_plane_rows >= d.Hi && d.impl != 1), "in_plane_rows %d (tensor-core path only, >= Hi)", d.in_plane_rows);
     PCX_REQUIRE(d.act != 1 || d_slope, "PReLU needs slopes");
+    PCX_REQUIRE(d.square_input == 0 || d.square_input == 1, "square_input %d", d.square_input);
+    PCX_REQUIRE(d.square_input == 0 || d.impl != 1, "square_input is implemented by the tensor-core path only");
     if (d_mul || d_residual)
         PCX_REQUIRE(d.aux_y0 >= 0 && d.aux_x0 >= 0 && d.aux_y0 + d.Ho <= d.aux_rows && d.aux_x0 + d.Wo <= d.aux_pitch, "aux window outside the aux plane");
     if (d.impl == 0 || d.impl == 2 || d.impl == 3) return pcx_conv2d_tc(desc, d_x, d_w, d_bias, d_slope, d_mul, d_residual, d_y, stream);

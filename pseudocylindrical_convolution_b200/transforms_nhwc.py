@@ -126,8 +126,9 @@ class Runner:
 
     # ------------------------------------------------------------------------------------------ ops
     def conv(self, x: View, weight, bias, k, stride, Co, out: View, wl_out, act=ACT_NONE, slope=None, mul: View = None,
-             residual: View = None, ci_pad=None, d2w=False):
-        """d2w: Dtow(2) fused into the store - `out` is the (2 Ho, 2 Wo, Co / 4) view the pixel shuffle would produce."""
+             residual: View = None, ci_pad=None, d2w=False, square_input=False):
+        """d2w: Dtow(2) fused into the store - `out` is the (2 Ho, 2 Wo, Co / 4) view the pixel shuffle would produce.
+        square_input: the convolution reads x * x, squared on chip (GDN)."""
         Ho, Wo = (x.h - k) // stride + 1, (x.W - k) // stride + 1
         if d2w:
             assert (2 * Ho, 2 * Wo) == (out.h, out.W) and 4 * out.C == Co and mul is None and residual is None
@@ -139,6 +140,7 @@ class Runner:
         d.Co, d.Ho, d.Wo = Co, Ho, Wo
         d.out_rows, d.out_pitch, d.out_y0, d.out_x0 = out.rows, out.pitch, out.y0, out.x0
         d.k, d.stride, d.act, d.impl = k, stride, act, 3 if d2w else 2
+        d.square_input = 1 if square_input else 0
         aux = mul if mul is not None else residual
         if aux is not None:
             if mul is not None and residual is not None:
@@ -179,10 +181,9 @@ class Runner:
         """out = fill(residual + z / sqrt(beta' + gamma' z^2))   (inverse: z * sqrt(.)) - PseudoContextV2.py:186-216"""
         assert z.y0 == 0 and z.x0 == 0 and z.rows == z.h and z.pitch == z.W
         be, ge = gdn_module._effective()
-        z2 = self.plain(z.planes, z.h, z.W, z.C)
-        call("pcx_square", _p(z.buf), _p(z2.buf), z.buf.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
-        self.conv(z2, ge, be, 1, 1, z.C, out, wl, ACT_SQRT if gdn_module.inverse else ACT_RSQRT, None, z, residual)
-        self.release(z2)
+        # the 1x1 GEMM over z^2: z is squared inside the kernel's shared-memory pipeline (no x^2 tensor, no square kernel);
+        # the same z is the epilogue's gate operand
+        self.conv(z, ge, be, 1, 1, z.C, out, wl, ACT_SQRT if gdn_module.inverse else ACT_RSQRT, None, z, residual, square_input=True)
         return out
 
 

@@ -485,6 +485,39 @@ def test_conv_tensor_core_vs_direct(cuda, orc, Ci, Co, k, s, act, h, W):
     assert err.max() < 1e-2 * scale, "max err %g" % err.max()
 
 
+@pytest.mark.parametrize("act,Co,h,W", [(3, 192, 8, 128), (4, 192, 3, 72), (3, 96, 16, 520)])
+def test_conv_square_input_is_the_conv_of_the_square(cuda, act, Co, h, W):
+    """pcx_conv_desc.square_input (GDN / IGDN: the 1x1 GEMM over x^2, PseudoContextV2.py:186-216): squaring the activation stage
+    in the kernel's shared-memory pipeline gives bit for bit the result of the same kernel reading a materialised x * x."""
+    import ctypes as C
+    import torch
+    from pseudocylindrical_convolution_b200._lib import call
+    rng = np.random.default_rng(77)
+    Ci = Co
+    wl = [max(4, W - 9 * (g % 4)) for g in range(16)]
+    x = torch.from_numpy(rng.standard_normal((32, h, W, Ci)).astype(np.float32)).to(cuda)           # two images, NHWC
+    w = torch.from_numpy((rng.random((Co, Ci, 1, 1)) * 0.02).astype(np.float32)).to(cuda)
+    b = torch.from_numpy((1.0 + rng.random(Co)).astype(np.float32)).to(cuda)
+    res = torch.from_numpy(rng.standard_normal((32, h, W, Co)).astype(np.float32)).to(cuda)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    outs = []
+    for fused in (0, 1):
+        d, Ho, Wo = _conv_desc(32, Ci, h, W, Co, 1, 1, act, wl, 0)
+        d.square_input = fused
+        y = torch.full((32, h, W, Co), -3.0, device=cuda)
+        call("pcx_conv2d_fwd", C.byref(d), P(x if fused else x * x), P(w), P(b), None, P(x), P(res), P(y), None)
+        outs.append(y)
+    torch.cuda.synchronize()
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1])
+    # and the flag is refused where it has no meaning
+    d, _, _ = _conv_desc(32, Ci, h, W, Co, 1, 1, 1, wl, 0)
+    d.square_input = 1
+    from pseudocylindrical_convolution_b200._lib import PcxError
+    with pytest.raises(PcxError):
+        call("pcx_conv2d_fwd", C.byref(d), P(x), P(w), P(b), P(b), None, None, P(outs[0]), None)
+
+
 @pytest.mark.parametrize("k,h,W", [(3, 6, 256), (1, 5, 72), (3, 4, 640)])
 def test_conv_fused_depth_to_space(cuda, k, h, W):
     """pcx_conv2d_fwd impl 3 (Dtow(2) folded into the store of a 192 -> 768 convolution: ResidualBlockUp conv1 / short_cut,
