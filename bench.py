@@ -222,7 +222,7 @@ def run_reference(args):
             "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
             "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -466,6 +466,9 @@ def run_gpu(args):
                     "traffic": None, "peak_source": "%s bf16_tflops_sustained / 2 (kind::tf32 issues at half the f16 rate)" % peaks["source"],
                     "peak_burst": peaks["bf16"] / 2.0, "flops_per_step": flops_step, "conv_ms_per_step": conv_ms,
                     "share_of_step": conv_ms / (sec_rank * 1e3),
+                    "classes": [{"k": k[0], "stride": k[1], "Ci": k[2], "Co": k[3], "launches_per_step": c[2] // args.steps,
+                                 "ms_per_step": c[0] / args.steps, "TFLOP/s": c[1] / (c[0] / 1e3) / 1e12}
+                                for k, c in sorted(classes.items(), key=lambda kv: -kv[1][0])],
                     "note": "algorithmic FLOPs (SURVEY.md 8d: 686.7 + 845.4 kFLOP per ERP pixel, valid cells) / summed CUDA-event time of every pcx_conv2d_fwd launch of the timed steps; "
                             "the layers include the HBM-bound 1x1 / GDN convolutions"}
 
@@ -557,7 +560,7 @@ def run_gpu(args):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_all_convs": roofline_all,
                 "roofline_latency": roofline_latency,
                 "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "stages": stages, "large_configs": extras, "tile_pipeline": tile}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -597,6 +600,20 @@ def time_large(enc, dec, dev, tmpd):
     return res
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """the one JSON line, on the process's original stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -609,6 +626,12 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-tile", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: libraries that write to file descriptor 1 on their own (NCCL prints its
+    # version there at communicator creation) are sent to stderr for the duration of the run
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
