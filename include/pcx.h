@@ -47,7 +47,7 @@ enum {
 };
 
 /* ---- library ------------------------------------------------------------------------------------ */
-int pcx_abi_version(void);
+int pcx_abi_version(void);   /* 2: pcx_conv_desc carries square_input */
 const char *pcx_last_error(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 long long pcx_launch_count(void);

@@ -199,18 +199,6 @@ __device__ __forceinline__ StepTap step_tap_of(const StepTapOff &o, const float 
     return r;
 }
 
-// L2 load that keeps its program order among its kind (volatile asm), and a zero-instruction fence that makes seven loaded
-// values "used": together they force a batch of loads to be issued back to back before any dependent arithmetic.
-__device__ __forceinline__ float ld_cg_ordered(const float *p)
-{
-    float v;
-    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void reg_fence7(float (&a)[7])
-{
-    asm volatile("" : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]));
-}
 // NQ consecutive 128-bit loads from one base address in ONE asm statement (one predicate, immediate offsets, issued back to
 // back; volatile keeps them ahead of the arithmetic that follows).  With on == 0 nothing is loaded and v is left untouched -
 // the caller never consumes it.  L1-cached (.ca) on purpose: inside one launch every scratch buffer is written in exactly one
@@ -323,29 +311,6 @@ __device__ __noinline__ float flow_poll(const float *p, FlowCtl *ctl)
     }
     return __uint_as_float(v);
 }
-// v[ul * GI + m], m < GI (ul is a run-time index: selected by predication so that v stays in registers) <- polled values of p[m]
-template <int GI>
-__device__ __forceinline__ void flow_validate(float (&v)[8 * GI], int ul, const float *p, FlowCtl *ctl)
-{
-    bool bad = false;
-#pragma unroll
-    for (int u = 0; u < 8; u++)
-#pragma unroll
-        for (int m = 0; m < GI; m++) bad = bad || (u == ul && __float_as_uint(v[u * GI + m]) == FLOW_SENTINEL);
-    if (!bad) return;
-    float f[GI];
-#pragma unroll
-    for (int m = 0; m < GI; m++) f[m] = flow_ld(p + m);              // all GI re-reads in flight together: one round trip when ready
-#pragma unroll
-    for (int m = 0; m < GI; m++)
-        if (__float_as_uint(f[m]) == FLOW_SENTINEL) f[m] = flow_poll(p + m, ctl);
-#pragma unroll
-    for (int u = 0; u < 8; u++)
-#pragma unroll
-        for (int m = 0; m < GI; m++)
-            if (u == ul) v[u * GI + m] = f[m];
-}
-
 // One warp per cell.  Lane = filter tap (kh, kw) (25 live lanes); it runs the GI chains of its tap - the reference's virtual
 // lanes m*25 + tap - over the allowed channel groups in ascending order, 8 groups per batch of 128-bit loads.  The chain sums
 // are then moved to the virtual-lane positions (lane t takes lanes t, t+32, t+64 of the reference block) and folded exactly

@@ -46,7 +46,7 @@ int pcx_sm_count()
 
 extern "C" {
 
-int pcx_abi_version(void) { return 1; }
+int pcx_abi_version(void) { return 2; }
 const char *pcx_last_error(void) { return g_err; }
 long long pcx_launch_count(void) { return g_pcx_launches.load(); }
 
