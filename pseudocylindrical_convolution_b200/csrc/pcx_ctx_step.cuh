@@ -16,11 +16,13 @@ namespace {
 // w: mixture logits on entry, softmax weights on return; d: raw deltas on entry, clamped on return; c[0..nstep]: the table.
 // NGC / NSC > 0 fix the mixture size / number of steps at compile time (every loop unrolls, the arrays live in registers);
 // 0 takes the run-time value.  One source for both so that the expression shapes - and the bits - are the same.
-template <int NGC, int NSC>
-__device__ __forceinline__ void gmm_cdf_row(float *w, float *d, const float *mu, int ng_rt, int nstep_rt, float bias, float total,
-                                            float beta, int form, float *c)
+// The row is built from three pieces so that a row can also be spread over the lanes of a thread group (gmm_boundary is the
+// expensive part - a division, an erf and two double FMAs per mixture component): the persistent decoder kernel gives every
+// boundary of a row its own lane.  gmm_cdf_row is the three pieces in sequence - one source, identical bits either way.
+template <int NGC>
+__device__ __forceinline__ void gmm_prepare(float *w, float *d, int ng_rt, float beta)
 {
-    const int ng = NGC > 0 ? NGC : ng_rt, nstep = NSC > 0 ? NSC : nstep_rt;
+    const int ng = NGC > 0 ? NGC : ng_rt;
     float mval = -1e10f, psum = 0.f;
 #pragma unroll
     for (int i = 0; i < ng; i++)
@@ -37,31 +39,40 @@ __device__ __forceinline__ void gmm_cdf_row(float *w, float *d, const float *mu,
         t = t < 0 ? beta : t + beta;
         d[i] = t;
     }
+}
+// c[pt], 1 <= pt < nstep, from the prepared weights / deltas
+template <int NGC>
+__device__ __forceinline__ float gmm_boundary(const float *w, const float *d, const float *mu, int ng_rt, int pt, float bias, float total,
+                                              int form)
+{
+    const int ng = NGC > 0 ? NGC : ng_rt;
     const float s2 = (float)(1. / sqrt(2.0));
+    float v = pt - 1 - bias + 0.5;
+    float ps = 0;
+    if (form == 0) {
+        // entropy_gmm_table_batch_forward_kernel (:146-150): the whole term stays in double, one rounding per component
+#pragma unroll
+        for (int i = 0; i < ng; i++) {
+            ps = ps + w[i] * (0.5 + 0.5 * erf(s2 * (v - mu[i]) / d[i]));
+        }
+    } else {
+        // entropy_gmm_table_forward_kernel (:69-72): f is stored to float first, then a float FFMA
+        float f;
+#pragma unroll
+        for (int i = 0; i < ng; i++) {
+            f = 0.5 + 0.5 * erf(s2 * (v - mu[i]) / d[i]);
+            ps = ps + w[i] * f;
+        }
+    }
+    return (float)static_cast<int>(total * ps + 0.5);
+}
+// strict-monotonic fix-up (:83-105), on integer-valued floats as the reference does; c[0] and c[nstep] are set here
+template <int NSC>
+__device__ __forceinline__ void gmm_fixup(float *c, int nstep_rt, float total)
+{
+    const int nstep = NSC > 0 ? NSC : nstep_rt;
     c[0] = 0.f;
     c[nstep] = (float)static_cast<int>(total);
-#pragma unroll
-    for (int pt = 1; pt < nstep; pt++) {
-        float v = pt - 1 - bias + 0.5;
-        float ps = 0;
-        if (form == 0) {
-            // entropy_gmm_table_batch_forward_kernel (:146-150): the whole term stays in double, one rounding per component
-#pragma unroll
-            for (int i = 0; i < ng; i++) {
-                ps = ps + w[i] * (0.5 + 0.5 * erf(s2 * (v - mu[i]) / d[i]));
-            }
-        } else {
-            // entropy_gmm_table_forward_kernel (:69-72): f is stored to float first, then a float FFMA
-            float f;
-#pragma unroll
-            for (int i = 0; i < ng; i++) {
-                f = 0.5 + 0.5 * erf(s2 * (v - mu[i]) / d[i]);
-                ps = ps + w[i] * f;
-            }
-        }
-        c[pt] = (float)static_cast<int>(total * ps + 0.5);
-    }
-    // strict-monotonic fix-up (:83-105), on integer-valued floats as the reference does
     float fb = 0.f, mv = 0.f;
     int midx = 0;
 #pragma unroll
@@ -75,6 +86,16 @@ __device__ __forceinline__ void gmm_cdf_row(float *w, float *d, const float *mu,
         for (int i = 0; i < nstep; i++)
             if (i >= midx) c[i + 1] -= fb;
     }
+}
+template <int NGC, int NSC>
+__device__ __forceinline__ void gmm_cdf_row(float *w, float *d, const float *mu, int ng_rt, int nstep_rt, float bias, float total,
+                                            float beta, int form, float *c)
+{
+    const int nstep = NSC > 0 ? NSC : nstep_rt;
+    gmm_prepare<NGC>(w, d, ng_rt, beta);
+#pragma unroll
+    for (int pt = 1; pt < nstep; pt++) c[pt] = gmm_boundary<NGC>(w, d, mu, ng_rt, pt, bias, total, form);
+    gmm_fixup<NSC>(c, nstep_rt, total);
 }
 
 

@@ -327,26 +327,43 @@ __global__ void __launch_bounds__(NT, BPS) wave_flow_kernel(const __grid_constan
             const StepLayer &last = d.L[d.nlayers - 1];
             const i64 net_stride = (i64)d.nimg * d.npart * h * W * last.cp_out;
             uint4 *rows = f.rows + (size_t)img * f.rows_cap;
-            for (int k = bi + B * tid; k < count; k += B * NT) {
-                const int4 ci = d.cell[first + k];
-                const int tw = ci.x, hp = ci.y, g = ci.z, th = ci.w;
-                const int tc = step - tw - hp;
-                const float *pp = last.out + ((((i64)img * d.npart + g) * h + th) * W + tw) * last.cp_out + tc * 3;
-                float v[9];
+            // eight lanes per row: lane j builds boundary j + 1 (the expensive part: per mixture component a division, an erf and
+            // two double FMAs), the seven values meet through shuffles and every lane runs the cheap fix-up; lane 0 stores.  The
+            // row is on the serial path of the step - the host cannot start before it - so its latency, not its work, counts.
+            const int sub = tid & 7, grp = tid >> 3;
+            const int rounds = (count - bi + B * (NT >> 3) - 1) / (B * (NT >> 3));        // the same for every thread of the block
+            for (int it = 0; it < rounds; it++) {
+                const int k = bi + B * (grp + it * (NT >> 3));
+                const bool valid = k < count;
+                float cpt = 0.f;
+                if (valid) {
+                    const int4 ci = d.cell[first + k];
+                    const int tw = ci.x, hp = ci.y, g = ci.z, th = ci.w;
+                    const int tc = step - tw - hp;
+                    const float *pp = last.out + ((((i64)img * d.npart + g) * h + th) * W + tw) * last.cp_out + tc * 3;
+                    float v[9];
 #pragma unroll
-                for (int j = 0; j < 9; j++) v[j] = flow_ld(pp + (j / 3) * net_stride + (j % 3));   // nets: logits, delta, mean
+                    for (int j = 0; j < 9; j++) v[j] = flow_ld(pp + (j / 3) * net_stride + (j % 3));   // nets: logits, delta, mean
 #pragma unroll
-                for (int j = 0; j < 9; j++)
-                    if (__float_as_uint(v[j]) == FLOW_SENTINEL) v[j] = flow_poll(pp + (j / 3) * net_stride + (j % 3), &ctl);
-                float w[3] = {v[0], v[1], v[2]}, dl[3] = {v[3], v[4], v[5]}, mu[3] = {v[6], v[7], v[8]}, c[9];
-                gmm_cdf_row<3, 8>(w, dl, mu, 3, 8, d.gmm_bias, d.gmm_total, d.gmm_beta, 0, c);
-                uint4 r;
-                r.x = (unsigned)(int)c[1] | ((unsigned)(int)c[2] << 16);
-                r.y = (unsigned)(int)c[3] | ((unsigned)(int)c[4] << 16);
-                r.z = (unsigned)(int)c[5] | ((unsigned)(int)c[6] << 16);
-                r.w = (unsigned)(int)c[7] | ((0x8000u | ((f.tag_salt + (unsigned)step) & 0x7fffu)) << 16);
-                asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(rows + k), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w)
-                             : "memory");
+                    for (int j = 0; j < 9; j++)
+                        if (__float_as_uint(v[j]) == FLOW_SENTINEL) v[j] = flow_poll(pp + (j / 3) * net_stride + (j % 3), &ctl);
+                    float w[3] = {v[0], v[1], v[2]}, dl[3] = {v[3], v[4], v[5]}, mu[3] = {v[6], v[7], v[8]};
+                    gmm_prepare<3>(w, dl, 3, d.gmm_beta);
+                    cpt = gmm_boundary<3>(w, dl, mu, 3, sub < 7 ? sub + 1 : 7, d.gmm_bias, d.gmm_total, 0);
+                }
+                float c[9];
+#pragma unroll
+                for (int j = 1; j < 8; j++) c[j] = __shfl_sync(0xffffffffu, cpt, (tid & 24) + j - 1);
+                gmm_fixup<8>(c, 8, d.gmm_total);
+                if (valid && sub == 0) {
+                    uint4 r;
+                    r.x = (unsigned)(int)c[1] | ((unsigned)(int)c[2] << 16);
+                    r.y = (unsigned)(int)c[3] | ((unsigned)(int)c[4] << 16);
+                    r.z = (unsigned)(int)c[5] | ((unsigned)(int)c[6] << 16);
+                    r.w = (unsigned)(int)c[7] | ((0x8000u | ((f.tag_salt + (unsigned)step) & 0x7fffu)) << 16);
+                    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(rows + k), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w)
+                                 : "memory");
+                }
             }
         }
         if (tracer) f.trace[(size_t)step * 16 + 15] = flow_now();
