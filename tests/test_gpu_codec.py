@@ -295,6 +295,15 @@ def test_fused_step_decoder_equals_operator_sequence(codec, tmp_path):
                 assert torch.equal(dec.ent.decode_batch(H // 128, W // 8, names), sym), "threads=%d" % nthreads
             finally:
                 lib.pcx_flow_set_threads(prev)
+        # both forms of the dataflow kernel (256 threads x 2 blocks per SM, 128 x 4) on the same streams, whatever the automatic choice
+        for form in ("0", "1"):
+            os.environ["PCX_FLOW_FORM"] = form
+            try:
+                assert torch.equal(dec.ent.decode_batch(H // 128, W // 8, names), sym), "kernel form %s" % form
+                dec.ent.start(names[2])
+                assert torch.equal(dec.ent(H // 128, W // 8), sym[32:48]), "kernel form %s, single image" % form
+            finally:
+                del os.environ["PCX_FLOW_FORM"]
     finally:
         lib.pcx_wave_set_fused(2)
 
