@@ -16,7 +16,8 @@ WAVE_IMPL = int(os.environ.get("PCX_WAVE_IMPL", "1"))
 # 0 = the stepwise loop (pcx_wave_encode).  Same per-scalar arithmetic, byte-identical bitstreams.
 WAVE_ENCODE_FULL = int(os.environ.get("PCX_WAVE_ENCODE_FULL", "1"))
 # rows (symbols) per image in one chunk of the one-shot encoder's CDF stream: the host codes chunk i while chunk i+1 is computed
-WAVE_CHUNK_ROWS = int(os.environ.get("PCX_WAVE_CHUNK_ROWS", str(1 << 17)))
+# (8 x 512x1024, 93 K rows per image, entropy encode in ms: one chunk 11.9, 64 K rows per chunk 10.9-11.2, 8 K .. 32 K 10.8-11.9)
+WAVE_CHUNK_ROWS = int(os.environ.get("PCX_WAVE_CHUNK_ROWS", str(1 << 16)))
 
 # capture the channels-last analysis / synthesis transforms into CUDA graphs (transforms_nhwc._run_graphed)
 CUDA_GRAPHS = os.environ.get("PCX_CUDA_GRAPHS", "1") != "0"
