@@ -141,6 +141,9 @@ __device__ __noinline__ unsigned flow_poll_symbol(const FlowNet &f, const unsign
 // Measured alternatives to the warp-per-cell task that are NOT in this file any more (bit-identical, all slower on the B200;
 // numbers in profiles/r2c_flow_task_probe.txt): four lanes per task, C = 2 / 3 cells per warp sharing the weight loads, a
 // member-major layout with the loads of member m + 1 issued under the FFMAs of member m, L1 prefetch of the next task's operands.
+// Also measured and dropped in round 2 (DESIGN.md section 3.3 has the numbers): operands staged in shared memory with cp.async, a
+// branch-free FFMA batch, three and five blocks per SM at 80 / 96 registers, and a lane-per-cell form (a lane runs the 75 chains
+// of its cell, fold tree on an in-lane stack: 3.5x fewer instructions, 12x slower - one exposed L2 round trip per chain).
 // NT threads per block, BPS blocks per SM, the first CACHE cells of a block's step resolved in shared memory.  Two forms are
 // built: 256 x 2 (cache 64) when a layer of a step is about one task per warp (one small image: fewest blocks to rendezvous
 // per weight change), 128 x 4 (cache 32) when every warp has several tasks per layer (batches, large images): smaller blocks
