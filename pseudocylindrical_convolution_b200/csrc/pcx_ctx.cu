@@ -54,19 +54,34 @@ __global__ void ctx_pad_kernel(float *__restrict__ buf, Bands bands, const int *
     i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     i64 total = (i64)nitems * cpn * nrep * (full ? C / cpn : 1);
     if (idx >= total) return;
-    int it = (int)(idx % nitems);
-    int cc = (int)((idx / nitems) % cpn);
-    i64 n = idx / nitems / cpn;
+    int it, cc, grp_full = 0;
+    i64 n;
+    const int G = C / cpn;
+    if (total < (1ll << 31)) {                         // the usual case: 32-bit divisions (a 64-bit one costs ~100 instructions)
+        const unsigned u = (unsigned)idx, a = u / (unsigned)nitems, b = a / (unsigned)cpn;
+        it = (int)(u - a * (unsigned)nitems);
+        cc = (int)(a - b * (unsigned)cpn);
+        unsigned nn = b;
+        if (full) {
+            const unsigned c2 = b / (unsigned)G;
+            grp_full = (int)(b - c2 * (unsigned)G);
+            nn = c2;
+        }
+        n = nn;
+    } else {
+        it = (int)(idx % nitems);
+        cc = (int)((idx / nitems) % cpn);
+        n = idx / nitems / cpn;
+        if (full) {
+            grp_full = (int)(n % G);
+            n /= G;
+        }
+    }
     int4 I = items[first + it];
     if (kind >= 0 && I.x != kind) return;
     const int npart = bands.npart;
     const i64 oh = h + 2 * pad, ow = W + 2 * pad;
-    int grp = psum - I.w;
-    if (full) {
-        const int G = C / cpn;
-        grp = (int)(n % G);
-        n /= G;
-    }
+    const int grp = full ? grp_full : psum - I.w;
     i64 c = (i64)grp * cpn + cc;
     if (I.x == 0) {
         int e = I.y, hr = I.z;

@@ -25,20 +25,22 @@ __global__ void halo_fill_nhwc_kernel(float *__restrict__ buf, const int *__rest
     const i64 img = plane / npart;
     const int wl = bands.wl[g];
     const int ringw = wl + 2 * pad;
-    const i64 ncell = (i64)2 * pad * ringw + (i64)2 * pad * h;
+    const int ncell = 2 * pad * ringw + 2 * pad * h;           // ring cells of one plane: 32-bit index arithmetic (the host checks)
     const i64 C = (i64)P.C4 * 4;
-    for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < ncell * P.C4; idx += (i64)gridDim.x * blockDim.x) {
-        const int c4 = (int)(idx % P.C4);
-        const i64 cell = idx / P.C4;
+    const int total = ncell * P.C4;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int cell = idx / P.C4;
+        const int c4 = idx - cell * P.C4;
         int ty, tx;                                  // position inside the padded tile
-        if (cell < (i64)2 * pad * ringw) {           // halo rows (full ring width)
-            const int rr = (int)(cell / ringw);
-            tx = (int)(cell % ringw);
+        if (cell < 2 * pad * ringw) {                // halo rows (full ring width)
+            const int rr = cell / ringw;
+            tx = cell - rr * ringw;
             ty = rr < pad ? rr : h + rr;             // rr in [pad, 2 pad) -> rows h+pad .. h+2pad-1
         } else {                                     // left / right columns of the interior rows
-            const i64 k = cell - (i64)2 * pad * ringw;
-            ty = pad + (int)(k / (2 * pad));
-            const int j = (int)(k % (2 * pad));
+            const int k = cell - 2 * pad * ringw;
+            const int row = k / (2 * pad);
+            ty = pad + row;
+            const int j = k - row * (2 * pad);
             tx = j < pad ? j : wl + j;
         }
         // logical column with the longitude wrap
@@ -127,6 +129,7 @@ int pcx_halo_fill_nhwc(float *d_buf, int N, int C, int h, int W, int npart, int 
     P.planes = (i64)N * npart;
     PCX_REQUIRE(P.planes <= 65535, "too many planes");
     const i64 work = ((i64)2 * pad * (wmax + 2 * pad) + (i64)2 * pad * h) * P.C4;
+    PCX_REQUIRE(work < (1ll << 30), "halo ring too large for 32-bit indexing");
     int bx = ceil_div(work, 256);
     if (bx > 1024) bx = 1024;
     halo_fill_nhwc_kernel<<<dim3(bx, (unsigned)P.planes), 256, 0, (cudaStream_t)stream>>>(d_buf, d_band, d_row, d_col, d_tw, b, P);
